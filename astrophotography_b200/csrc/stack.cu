@@ -1,0 +1,568 @@
+// Frame-stack reducer (sm_100a): per-pixel median / sigma-clipped mean over N frames.
+//
+// Replaces ccdproc.combine(...) as called by the reference at
+// AstroPhotography/scripts/ap_combine_darks.py:411-420 (settings :394-399) and
+// generalises it to astropy.stats.sigma_clip's iterative kappa-sigma clip.
+//
+// Layout: N separate H x W float32 frames (frame-major; never transposed in
+// HBM).  One thread owns one pixel; a warp reads 128 contiguous bytes of each
+// frame, so every HBM access is a full coalesced line and each input byte is
+// read exactly once (4*N + 5 B per pixel algorithmic traffic).
+//
+// Three kernel families behind one entry point:
+//   generic<CAP>      every parameter combination, N <= 1024.  float64
+//                     arithmetic in the oracle's operation order (explicitly
+//                     rounded intrinsics, no FMA contraction): bit-identical to
+//                     the numpy restatement.  Values live in local memory.
+//   meanclip<NB,NLO>  iterative kappa-sigma clip about the MEAN with the
+//                     population STD, then the mean of the survivors.
+//                     Register-resident (N <= 200), float32 arithmetic on
+//                     pivot-shifted values with a rigorous error bound: a pixel
+//                     whose decision could differ from the float64 oracle
+//                     (a sample within the bound of a clip threshold) is redone
+//                     by the generic routine, so rejection maps are identical.
+//   sorted<NB,MODE>   register-resident Batcher merge-exchange network
+//                     (N <= 128): plain median (MODE_MED), or the reference's
+//                     ApMasterCal setting -- one median/MAD clip pass then the
+//                     mean (MODE_MEDMAD1) -- with the sorted column parked in
+//                     shared memory for the data-dependent MAD selection.
+//   A pixel holding NaN/inf samples leaves the fast kernels for the generic
+//   routine, which owns the reference's non-finite semantics.
+#include <float.h>
+#include <math.h>
+
+#include "apgpu_common.cuh"
+#include "sort_networks.inc"
+
+namespace {
+
+constexpr double MAD_TO_STD = 1.482602218505602;   // astropy.stats.mad_std scale
+constexpr int TPB = 128;                           // threads (= pixels) per block
+
+struct StackArgs {
+    int N, method, maxiters, cen, dev;
+    double klo, khi;
+    int64_t pix0, npix;          // flat pixel range [pix0, pix0 + npix)
+    void* out; int out_f64;
+    void* nrej; int nrej_u16;
+    void* uncert;
+    uint8_t* allmasked;
+};
+
+template <int CAP> struct FramePtrs { const float* p[CAP]; };
+
+__device__ __forceinline__ bool finite_f(float x) { return fabsf(x) <= FLT_MAX; }
+
+__device__ __forceinline__ void write_pixel(const StackArgs& a, int64_t p, double data, int nrej,
+                                            double unc, int allm) {
+    if (a.out_f64) reinterpret_cast<double*>(a.out)[p] = data;
+    else st_stream(reinterpret_cast<float*>(a.out) + p, (float)data);
+    if (a.nrej) {
+        if (a.nrej_u16) reinterpret_cast<uint16_t*>(a.nrej)[p] = (uint16_t)nrej;
+        else reinterpret_cast<uint8_t*>(a.nrej)[p] = (uint8_t)nrej;
+    }
+    if (a.uncert) {
+        if (a.out_f64) reinterpret_cast<double*>(a.uncert)[p] = unc;
+        else reinterpret_cast<float*>(a.uncert)[p] = (float)unc;
+    }
+    if (a.allmasked) a.allmasked[p] = (uint8_t)allm;
+}
+
+// ---------------------------------------------------------------------------
+// generic routine: float64, oracle operation order
+// ---------------------------------------------------------------------------
+__device__ void shell_sort(float* s, int n) {
+    const int gaps[8] = {701, 301, 132, 57, 23, 10, 4, 1};
+    for (int g = 0; g < 8; ++g) {
+        int gap = gaps[g];
+        if (gap >= n && gap != 1) continue;
+        for (int i = gap; i < n; ++i) {
+            float t = s[i];
+            int j = i;
+            while (j >= gap && s[j - gap] > t) { s[j] = s[j - gap]; j -= gap; }
+            s[j] = t;
+        }
+    }
+}
+
+// median of the sorted range s[sa, sb): nanmedian's (lo + hi) / 2 in float64
+__device__ __forceinline__ double median_sorted(const float* s, int sa, int sb) {
+    int m = sb - sa;
+    if (m <= 0) return (double)NAN;
+    double lo = (double)s[sa + ((m - 1) >> 1)];
+    if (m & 1) return lo;
+    double hi = (double)s[sa + (m >> 1)];
+    return __dmul_rn(__dadd_rn(lo, hi), 0.5);
+}
+
+// median of |x - med| over the sorted range: the deviations left of the median
+// grow towards sa and those right of it grow towards sb, so the k-th smallest
+// comes out of a two-pointer merge -- no second sort.
+__device__ __forceinline__ double mad_sorted(const float* s, int sa, int sb, double med) {
+    int m = sb - sa;
+    if (m <= 0) return (double)NAN;
+    int l = sa + ((m - 1) >> 1), r = l + 1;
+    int k1 = (m - 1) >> 1, k2 = m >> 1;
+    double d1 = 0.0, d2 = 0.0;
+    for (int t = 0; t <= k2; ++t) {
+        double dl = (l >= sa) ? fabs(__dsub_rn((double)s[l], med)) : (double)INFINITY;
+        double dr = (r < sb) ? fabs(__dsub_rn((double)s[r], med)) : (double)INFINITY;
+        double d;
+        if (dl <= dr) { d = dl; --l; } else { d = dr; ++r; }
+        if (t == k1) d1 = d;
+        if (t == k2) d2 = d;
+    }
+    return (m & 1) ? d1 : __dmul_rn(__dadd_rn(d1, d2), 0.5);
+}
+
+template <int CAP>
+__device__ __noinline__ void generic_pixel(const FramePtrs<CAP>& fp, const StackArgs& a, int64_t p) {
+    float v[CAP];      // frame order; NaN marks a sample that is not (or no longer) used
+    float s[CAP];      // the used samples, ascending
+    const int N = a.N;
+    const bool clip = a.maxiters != 0;
+    const bool need_sorted = (a.method != APGPU_METHOD_AVERAGE) ||
+                             (clip && (a.cen == APGPU_CEN_MEDIAN || a.dev == APGPU_DEV_MAD_STD));
+    int nk = 0;
+    for (int i = 0; i < N; ++i) {
+        float x = ld_stream(fp.p[i] + p);
+        // sigma_clip rejects non-finite samples up front; without clipping the
+        // nan-functions only skip NaN.
+        bool ok = clip ? finite_f(x) : (x == x);
+        v[i] = ok ? x : NAN;
+        if (ok) { if (need_sorted) s[nk] = x; ++nk; }
+    }
+    if (need_sorted) shell_sort(s, nk);
+    int sa = 0, sb = nk;
+
+    auto mean_kept = [&](int cnt) -> double {          // np.nanmean: sequential sum / count
+        double acc = 0.0;
+        for (int i = 0; i < N; ++i) if (v[i] == v[i]) acc = __dadd_rn(acc, (double)v[i]);
+        return __ddiv_rn(acc, (double)cnt);
+    };
+    auto std_kept = [&](int cnt, double avg) -> double {   // np.nanstd, ddof=0
+        double acc = 0.0;
+        for (int i = 0; i < N; ++i)
+            if (v[i] == v[i]) { double d = __dsub_rn((double)v[i], avg); acc = __dadd_rn(acc, __dmul_rn(d, d)); }
+        return __dsqrt_rn(__ddiv_rn(acc, (double)cnt));
+    };
+
+    if (clip) {
+        int it = 0;
+        while (a.maxiters < 0 || it < a.maxiters) {
+            ++it;
+            if (nk == 0) break;
+            double avg = 0.0, med = 0.0;
+            if (a.cen == APGPU_CEN_MEAN || a.dev == APGPU_DEV_STD) avg = mean_kept(nk);
+            if (a.cen == APGPU_CEN_MEDIAN || a.dev == APGPU_DEV_MAD_STD) med = median_sorted(s, sa, sb);
+            double c = (a.cen == APGPU_CEN_MEAN) ? avg : med;
+            double sd = (a.dev == APGPU_DEV_STD) ? std_kept(nk, avg)
+                                                 : __dmul_rn(MAD_TO_STD, mad_sorted(s, sa, sb, med));
+            double lo = __dsub_rn(c, __dmul_rn(sd, a.klo));
+            double hi = __dadd_rn(c, __dmul_rn(sd, a.khi));
+            int changed = 0;
+            for (int i = 0; i < N; ++i) {
+                float x = v[i];
+                if (x == x && ((double)x < lo || (double)x > hi)) { v[i] = NAN; ++changed; }
+            }
+            if (need_sorted) {
+                while (sa < sb && (double)s[sa] < lo) ++sa;
+                while (sa < sb && (double)s[sb - 1] > hi) --sb;
+            }
+            nk -= changed;
+            if (changed == 0) break;
+        }
+    }
+
+    double data, unc = (double)NAN;
+    if (nk == 0) {
+        data = (double)NAN;
+    } else if (a.method == APGPU_METHOD_AVERAGE) {
+        data = mean_kept(nk);
+    } else if (a.method == APGPU_METHOD_MEDIAN) {
+        data = median_sorted(s, sa, sb);
+    } else if (a.method == APGPU_METHOD_MIN) {
+        data = (double)s[sa];
+    } else {
+        data = (double)s[sb - 1];
+    }
+    if (a.uncert && nk > 0) {
+        double dev;
+        if (a.method == APGPU_METHOD_MEDIAN) {
+            dev = __dmul_rn(MAD_TO_STD, mad_sorted(s, sa, sb, median_sorted(s, sa, sb)));
+        } else {
+            dev = std_kept(nk, mean_kept(nk));
+        }
+        unc = __ddiv_rn(dev, __dsqrt_rn((double)nk));
+    }
+    write_pixel(a, p, data, N - nk, unc, nk == 0);
+}
+
+template <int CAP>
+__global__ void __launch_bounds__(TPB)
+stack_generic_kernel(const __grid_constant__ FramePtrs<CAP> fp, const __grid_constant__ StackArgs a) {
+    int64_t p = a.pix0 + (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (p >= a.pix0 + a.npix) return;
+    generic_pixel<CAP>(fp, a, p);
+}
+
+// ---------------------------------------------------------------------------
+// meanclip<NB, NLO>: kappa-sigma clip about the mean, N in (NLO, NB]
+// ---------------------------------------------------------------------------
+// i < NLO is known at compile time to be a real frame; only the NB-NLO tail
+// elements carry a (warp-uniform) runtime predicate.
+#define APGPU_ACTIVE(i) ((i) < NLO || (i) < N)
+
+__device__ __forceinline__ float med3(float a, float b, float c) {
+    return fmaxf(fminf(a, b), fminf(fmaxf(a, b), c));
+}
+
+template <int NB, int NLO>
+__global__ void __launch_bounds__(TPB)
+stack_meanclip_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_constant__ StackArgs a) {
+    const int64_t p = a.pix0 + (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (p >= a.pix0 + a.npix) return;
+    const int N = a.N;
+    float y[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) y[i] = APGPU_ACTIVE(i) ? ld_stream(fp.p[i] + p) : NAN;
+
+    // Pivot: median of the first three frames (robust to one outlier).  All
+    // further float32 arithmetic is on y = x - pivot, which keeps the sums
+    // small and the variance free of catastrophic cancellation.
+    const float pivot = med3(y[0], y[1], y[2]);
+    float z = 0.f;                       // NaN iff some sample is NaN/inf
+    float s1[4] = {0.f, 0.f, 0.f, 0.f};
+    float s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        if (APGPU_ACTIVE(i)) {
+            z = fmaf(y[i], 0.f, z);
+            float d = y[i] - pivot;
+            y[i] = d;
+            s1[i & 3] += d;
+            s2[i & 3] = fmaf(d, d, s2[i & 3]);
+        }
+    }
+    if (z != z) { generic_pixel<NB>(fp, a, p); return; }
+
+    int nk = N;
+    float S1 = (s1[0] + s1[1]) + (s1[2] + s1[3]);
+    float S2 = (s2[0] + s2[1]) + (s2[2] + s2[3]);
+    const float klo = (float)a.klo, khi = (float)a.khi;
+    const float kmax = fmaxf(klo, khi);
+    bool uncertain = false;
+    int it = 0;
+    while (a.maxiters != 0 && (a.maxiters < 0 || it < a.maxiters)) {
+        ++it;
+        if (S2 == 0.f) break;            // all survivors equal the pivot: bounds [c,c], nothing to reject
+        const float fn = (float)nk;
+        const float c = S1 / fn;
+        const float ex2 = S2 / fn;
+        const float var = ex2 - c * c;
+        const float sd = sqrtf(fmaxf(var, 0.f));
+        // Bound on |threshold_f32 - threshold_exact| + |y_f32 - y_exact|:
+        // summation over 4 interleaved accumulators, unit roundoff doubled for safety.
+        const float u2 = 1.1920929e-7f;                       // 2^-23
+        const float m = 0.25f * fn + 6.f;
+        const float g = m * u2 * (sqrtf(ex2) + 1.5f * kmax * ex2 / sd) + 6.f * u2 * (fabsf(c) + kmax * sd);
+        if (!(g < 0.25f * kmax * sd)) { uncertain = true; break; }   // degenerate (var ~ 0, NaN): let float64 decide
+        const float lo_out = (c - klo * sd) - g, lo_in = (c - klo * sd) + g;
+        const float hi_out = (c + khi * sd) + g, hi_in = (c + khi * sd) - g;
+        float n1[4] = {0.f, 0.f, 0.f, 0.f};
+        float n2[4] = {0.f, 0.f, 0.f, 0.f};
+        int kept = 0;
+        bool unc = false;
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const float d = y[i];
+            const bool keep = (d >= lo_out) && (d <= hi_out);     // NaN (already rejected / padding) fails
+            const bool sure = (d > lo_in) && (d < hi_in);
+            unc |= (keep != sure);
+            if (keep) {
+                ++kept;
+                n1[i & 3] += d;
+                n2[i & 3] = fmaf(d, d, n2[i & 3]);
+            } else {
+                y[i] = NAN;
+            }
+        }
+        if (unc) { uncertain = true; break; }
+        const bool changed = kept != nk;
+        nk = kept;
+        S1 = (n1[0] + n1[1]) + (n1[2] + n1[3]);
+        S2 = (n2[0] + n2[1]) + (n2[2] + n2[3]);
+        if (!changed || nk == 0) break;
+    }
+    if (uncertain || nk == 0) { generic_pixel<NB>(fp, a, p); return; }
+
+    // mean of the survivors = pivot + S1/nk, evaluated in float64: S1 is a sum
+    // of small shifted values, so its float32 error is ~1e-9 of the result.
+    double mean = __dadd_rn((double)pivot, __ddiv_rn((double)S1, (double)nk));
+    double unc_out = (double)NAN;
+    if (a.uncert) {
+        double cy = __ddiv_rn((double)S1, (double)nk);
+        double var = __dsub_rn(__ddiv_rn((double)S2, (double)nk), __dmul_rn(cy, cy));
+        unc_out = __ddiv_rn(__dsqrt_rn(var > 0.0 ? var : 0.0), __dsqrt_rn((double)nk));
+    }
+    write_pixel(a, p, mean, N - nk, unc_out, 0);
+}
+
+// ---------------------------------------------------------------------------
+// sorted<NB, NLO, MODE>: Batcher network in registers, N in (NLO, NB]
+// ---------------------------------------------------------------------------
+constexpr int MODE_MED = 0;       // method=median, no clipping
+constexpr int MODE_MEDMAD1 = 1;   // one median/MAD clip pass, then the mean (ApMasterCal)
+
+#define CE_X(i, j) { float lo_ = fminf(x[i], x[j]); float hi_ = fmaxf(x[i], x[j]); x[i] = lo_; x[j] = hi_; }
+
+template <int NB> __device__ __forceinline__ void sort_regs(float (&x)[NB]);
+#define APGPU_DEF_SORT(n) \
+    template <> __device__ __forceinline__ void sort_regs<n>(float (&x)[n]) { APGPU_SORTNET_##n(CE_X) }
+APGPU_DEF_SORT(4) APGPU_DEF_SORT(8) APGPU_DEF_SORT(12) APGPU_DEF_SORT(16) APGPU_DEF_SORT(20)
+APGPU_DEF_SORT(24) APGPU_DEF_SORT(32) APGPU_DEF_SORT(40) APGPU_DEF_SORT(48) APGPU_DEF_SORT(56)
+APGPU_DEF_SORT(64) APGPU_DEF_SORT(72) APGPU_DEF_SORT(80) APGPU_DEF_SORT(90) APGPU_DEF_SORT(100)
+APGPU_DEF_SORT(112) APGPU_DEF_SORT(128)
+
+template <int NB, int NLO, int MODE>
+__global__ void __launch_bounds__(TPB)
+stack_sorted_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_constant__ StackArgs a) {
+    extern __shared__ float col[];       // MODE_MEDMAD1: [NB][TPB] sorted columns
+    const int64_t p = a.pix0 + (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (p >= a.pix0 + a.npix) return;
+    const int N = a.N;
+    // Pad to NB with -inf / +inf split so that the real samples sit centred in
+    // the sorted array: the median is then at the compile-time index NB/2-1
+    // (and NB/2 for even N) whatever N is.
+    const int npad = NB - N;
+    const int nneg = npad >> 1;          // -inf pads; the other npad-nneg are +inf
+    float x[NB];
+    float z = 0.f;
+    double sum_all = 0.0;
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        if (APGPU_ACTIVE(i)) {
+            x[i] = ld_stream(fp.p[i] + p);
+        } else {
+            x[i] = (i - N < nneg) ? -INFINITY : INFINITY;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        if (APGPU_ACTIVE(i)) {
+            z = fmaf(x[i], 0.f, z);
+            if (MODE == MODE_MEDMAD1) sum_all = __dadd_rn(sum_all, (double)x[i]);   // frame order, as nanmean
+        }
+    }
+    if (z != z) { generic_pixel<NB>(fp, a, p); return; }
+
+    sort_regs<NB>(x);
+
+    constexpr int C = NB / 2;
+    const double med = (N & 1) ? (double)x[C - 1]
+                               : __dmul_rn(__dadd_rn((double)x[C - 1], (double)x[C]), 0.5);
+    if (MODE == MODE_MED) {
+        write_pixel(a, p, med, 0, (double)NAN, 0);
+        return;
+    }
+
+    // Park the sorted column in shared memory ([i][thread]: conflict-free for
+    // any per-thread index) for the data-dependent selection below.
+    float* s = col + threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < NB; ++i) s[i * TPB] = x[i];
+    const int base = nneg;               // real samples occupy [base, base + N)
+    // MAD by two-pointer merge outwards from the median (float64, exact).
+    int l = base + ((N - 1) >> 1), r = l + 1;
+    const int k1 = (N - 1) >> 1, k2 = N >> 1;
+    double d1 = 0.0, d2 = 0.0;
+    double dl = fabs(__dsub_rn((double)s[l * TPB], med));
+    double dr = (r < base + N) ? fabs(__dsub_rn((double)s[r * TPB], med)) : (double)INFINITY;
+    for (int t = 0; t <= k2; ++t) {
+        double d;
+        if (dl <= dr) {
+            d = dl; --l;
+            dl = (l >= base) ? fabs(__dsub_rn((double)s[l * TPB], med)) : (double)INFINITY;
+        } else {
+            d = dr; ++r;
+            dr = (r < base + N) ? fabs(__dsub_rn((double)s[r * TPB], med)) : (double)INFINITY;
+        }
+        if (t == k1) d1 = d;
+        if (t == k2) d2 = d;
+    }
+    const double mad = (N & 1) ? d1 : __dmul_rn(__dadd_rn(d1, d2), 0.5);
+    const double sd = __dmul_rn(MAD_TO_STD, mad);
+    const double lo = __dsub_rn(med, __dmul_rn(sd, a.klo));
+    const double hi = __dadd_rn(med, __dmul_rn(sd, a.khi));
+    int sa = base, sb = base + N;
+    while (sa < sb && (double)s[sa * TPB] < lo) ++sa;
+    while (sa < sb && (double)s[(sb - 1) * TPB] > hi) --sb;
+    const int nk = sb - sa;
+    double mean;
+    if (nk == N) {
+        mean = __ddiv_rn(sum_all, (double)N);
+    } else {
+        double acc = 0.0;
+        for (int i = sa; i < sb; ++i) acc = __dadd_rn(acc, (double)s[i * TPB]);
+        mean = __ddiv_rn(acc, (double)nk);      // nk >= 1: the median itself always survives
+    }
+    double unc = (double)NAN;
+    if (a.uncert) {
+        double acc = 0.0;
+        for (int i = sa; i < sb; ++i) {
+            double d = __dsub_rn((double)s[i * TPB], mean);
+            acc = __dadd_rn(acc, __dmul_rn(d, d));
+        }
+        unc = __ddiv_rn(__dsqrt_rn(__ddiv_rn(acc, (double)nk)), __dsqrt_rn((double)nk));
+    }
+    write_pixel(a, p, mean, N - nk, unc, 0);
+}
+
+// ---------------------------------------------------------------------------
+// host dispatch
+// ---------------------------------------------------------------------------
+enum Family { FAM_GENERIC = 0, FAM_MEANCLIP = 1, FAM_SORT_MED = 2, FAM_SORT_MEDMAD1 = 3 };
+
+struct Bucket { int nb, nlo; };
+// (NLO, NB] buckets.  meanclip goes to 200 frames in registers; sorted to 128.
+const Bucket MEANCLIP_BUCKETS[] = {{8, 2}, {16, 8}, {24, 16}, {32, 24}, {48, 32}, {64, 48}, {80, 64},
+                                   {100, 80}, {128, 100}, {160, 128}, {200, 160}};
+const Bucket SORT_BUCKETS[] = {{4, 0}, {8, 4}, {12, 8}, {16, 12}, {20, 16}, {24, 20}, {32, 24}, {40, 32},
+                               {48, 40}, {56, 48}, {64, 56}, {72, 64}, {80, 72}, {90, 80}, {100, 90},
+                               {112, 100}, {128, 112}};
+
+template <size_t K>
+const Bucket* find_bucket(const Bucket (&b)[K], int N) {
+    for (size_t i = 0; i < K; ++i) if (N > b[i].nlo && N <= b[i].nb) return &b[i];
+    return nullptr;
+}
+
+Family choose_family(int N, int method, double klo, double khi, int maxiters, int cen, int dev,
+                     bool want_uncert, int flags, const Bucket** bucket) {
+    *bucket = nullptr;
+    if (flags & APGPU_STACK_FORCE_GENERIC) return FAM_GENERIC;
+    if (method == APGPU_METHOD_AVERAGE && (maxiters == 0 || (cen == APGPU_CEN_MEAN && dev == APGPU_DEV_STD)) &&
+        N >= 3 && klo > 0.0 && khi > 0.0 && klo < 1e6 && khi < 1e6) {
+        if ((*bucket = find_bucket(MEANCLIP_BUCKETS, N))) return FAM_MEANCLIP;
+    }
+    if (method == APGPU_METHOD_MEDIAN && maxiters == 0 && !want_uncert) {
+        if ((*bucket = find_bucket(SORT_BUCKETS, N))) return FAM_SORT_MED;
+    }
+    if (method == APGPU_METHOD_AVERAGE && maxiters == 1 && cen == APGPU_CEN_MEDIAN &&
+        dev == APGPU_DEV_MAD_STD && N >= 2) {
+        if ((*bucket = find_bucket(SORT_BUCKETS, N))) return FAM_SORT_MEDMAD1;
+    }
+    return FAM_GENERIC;
+}
+
+template <int CAP>
+int launch_generic(const float* const* frames, const StackArgs& a, cudaStream_t st) {
+    FramePtrs<CAP> fp;
+    for (int i = 0; i < CAP; ++i) fp.p[i] = i < a.N ? frames[i] : nullptr;
+    int64_t blocks = (a.npix + TPB - 1) / TPB;
+    stack_generic_kernel<CAP><<<(unsigned)blocks, TPB, 0, st>>>(fp, a);
+    APGPU_LAUNCH_CHECK("stack_generic_kernel");
+    return APGPU_OK;
+}
+
+template <int NB, int NLO>
+int launch_meanclip(const float* const* frames, const StackArgs& a, cudaStream_t st) {
+    FramePtrs<NB> fp;
+    for (int i = 0; i < NB; ++i) fp.p[i] = i < a.N ? frames[i] : nullptr;
+    int64_t blocks = (a.npix + TPB - 1) / TPB;
+    stack_meanclip_kernel<NB, NLO><<<(unsigned)blocks, TPB, 0, st>>>(fp, a);
+    APGPU_LAUNCH_CHECK("stack_meanclip_kernel");
+    return APGPU_OK;
+}
+
+template <int NB, int NLO, int MODE>
+int launch_sorted(const float* const* frames, const StackArgs& a, cudaStream_t st) {
+    FramePtrs<NB> fp;
+    for (int i = 0; i < NB; ++i) fp.p[i] = i < a.N ? frames[i] : nullptr;
+    int64_t blocks = (a.npix + TPB - 1) / TPB;
+    size_t smem = (MODE == MODE_MEDMAD1) ? (size_t)NB * TPB * sizeof(float) : 0;
+    if (smem > 48 * 1024)
+        APGPU_CUDA(cudaFuncSetAttribute(stack_sorted_kernel<NB, NLO, MODE>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    stack_sorted_kernel<NB, NLO, MODE><<<(unsigned)blocks, TPB, smem, st>>>(fp, a);
+    APGPU_LAUNCH_CHECK("stack_sorted_kernel");
+    return APGPU_OK;
+}
+
+#define MC_CASE(NB_, NLO_) if (b->nb == NB_) return launch_meanclip<NB_, NLO_>(frames, a, st);
+#define SO_CASE(NB_, NLO_) if (b->nb == NB_) return launch_sorted<NB_, NLO_, MODE>(frames, a, st);
+
+int dispatch_meanclip(const Bucket* b, const float* const* frames, const StackArgs& a, cudaStream_t st) {
+    MC_CASE(8, 2) MC_CASE(16, 8) MC_CASE(24, 16) MC_CASE(32, 24) MC_CASE(48, 32) MC_CASE(64, 48)
+    MC_CASE(80, 64) MC_CASE(100, 80) MC_CASE(128, 100) MC_CASE(160, 128) MC_CASE(200, 160)
+    return APGPU_ERR_UNSUPPORTED;
+}
+
+template <int MODE>
+int dispatch_sorted(const Bucket* b, const float* const* frames, const StackArgs& a, cudaStream_t st) {
+    SO_CASE(4, 0) SO_CASE(8, 4) SO_CASE(12, 8) SO_CASE(16, 12) SO_CASE(20, 16) SO_CASE(24, 20)
+    SO_CASE(32, 24) SO_CASE(40, 32) SO_CASE(48, 40) SO_CASE(56, 48) SO_CASE(64, 56) SO_CASE(72, 64)
+    SO_CASE(80, 72) SO_CASE(90, 80) SO_CASE(100, 90) SO_CASE(112, 100) SO_CASE(128, 112)
+    return APGPU_ERR_UNSUPPORTED;
+}
+
+thread_local char g_kname[64];
+
+}  // namespace
+
+extern "C" const char* apgpu_stack_kernel_name(int N, int method, double k_lo, double k_hi,
+                                               int maxiters, int cen, int dev,
+                                               int want_uncert, int out_is_f64, int flags) {
+    (void)out_is_f64;
+    const Bucket* b = nullptr;
+    Family f = choose_family(N, method, k_lo, k_hi, maxiters, cen, dev, want_uncert != 0, flags, &b);
+    switch (f) {
+        case FAM_MEANCLIP: snprintf(g_kname, sizeof(g_kname), "meanclip<%d>", b->nb); break;
+        case FAM_SORT_MED: snprintf(g_kname, sizeof(g_kname), "sorted_median<%d>", b->nb); break;
+        case FAM_SORT_MEDMAD1: snprintf(g_kname, sizeof(g_kname), "sorted_medmad1<%d>", b->nb); break;
+        default: snprintf(g_kname, sizeof(g_kname), "generic<%d>", N <= 32 ? 32 : (N <= 128 ? 128 : 1024)); break;
+    }
+    return g_kname;
+}
+
+extern "C" int apgpu_stack_reduce_f32(const float* const* frames, int N, int64_t H, int64_t W,
+                                      int64_t row0, int64_t nrows, int method,
+                                      double k_lo, double k_hi, int maxiters, int cen, int dev,
+                                      void* out_data, int out_is_f64,
+                                      void* out_nrej, int nrej_is_u16,
+                                      void* out_uncert, uint8_t* out_allmasked,
+                                      int flags, apgpu_stream_t stream) {
+    APGPU_REQUIRE(frames && out_data, "stack_reduce: null frames/out pointer");
+    APGPU_REQUIRE(N >= 1 && N <= APGPU_STACK_MAX_FRAMES, "stack_reduce: N=%d outside 1..%d", N, APGPU_STACK_MAX_FRAMES);
+    APGPU_REQUIRE(H > 0 && W > 0 && row0 >= 0 && nrows >= 0 && row0 + nrows <= H,
+                  "stack_reduce: bad geometry H=%lld W=%lld row0=%lld nrows=%lld",
+                  (long long)H, (long long)W, (long long)row0, (long long)nrows);
+    APGPU_REQUIRE(method >= 0 && method <= 3, "stack_reduce: bad method %d", method);
+    APGPU_REQUIRE(cen == APGPU_CEN_MEAN || cen == APGPU_CEN_MEDIAN, "stack_reduce: bad cen %d", cen);
+    APGPU_REQUIRE(dev == APGPU_DEV_STD || dev == APGPU_DEV_MAD_STD, "stack_reduce: bad dev %d", dev);
+    APGPU_REQUIRE(maxiters == 0 || (k_lo == k_lo && k_hi == k_hi), "stack_reduce: NaN clip threshold");
+    APGPU_REQUIRE(!out_nrej || nrej_is_u16 || N <= 255, "stack_reduce: uint8 rejection map needs N <= 255 (N=%d)", N);
+    for (int i = 0; i < N; ++i) APGPU_REQUIRE(frames[i], "stack_reduce: frame %d is null", i);
+    if (nrows == 0) return APGPU_OK;
+
+    StackArgs a;
+    a.N = N; a.method = method; a.maxiters = maxiters; a.cen = cen; a.dev = dev;
+    a.klo = k_lo; a.khi = k_hi;
+    a.pix0 = row0 * W; a.npix = nrows * W;
+    a.out = out_data; a.out_f64 = out_is_f64;
+    a.nrej = out_nrej; a.nrej_u16 = nrej_is_u16;
+    a.uncert = out_uncert; a.allmasked = out_allmasked;
+    cudaStream_t st = (cudaStream_t)stream;
+
+    const Bucket* b = nullptr;
+    Family f = choose_family(N, method, k_lo, k_hi, maxiters, cen, dev, out_uncert != nullptr, flags, &b);
+    switch (f) {
+        case FAM_MEANCLIP: return dispatch_meanclip(b, frames, a, st);
+        case FAM_SORT_MED: return dispatch_sorted<MODE_MED>(b, frames, a, st);
+        case FAM_SORT_MEDMAD1: return dispatch_sorted<MODE_MEDMAD1>(b, frames, a, st);
+        default: break;
+    }
+    if (N <= 32) return launch_generic<32>(frames, a, st);
+    if (N <= 128) return launch_generic<128>(frames, a, st);
+    return launch_generic<1024>(frames, a, st);
+}

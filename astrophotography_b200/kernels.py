@@ -1,0 +1,213 @@
+"""Array-level entry points: torch CUDA tensors in, torch CUDA tensors out.
+
+Thin, validation-only wrappers over the C ABI (``include/apgpu.h``).  torch is
+used for device memory and streams only; every arithmetic operation of the hot
+path happens inside ``libapgpu.so``.  All calls are asynchronous on torch's
+current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes
+
+from . import _native
+
+METHODS = {"median": 0, "average": 1, "mean": 1, "min": 2, "max": 3}
+CENFUNCS = {"mean": 0, "median": 1}
+DEVFUNCS = {"std": 0, "mad_std": 1}
+_FORCE_GENERIC = 1
+
+
+def _stream(torch):
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _check_image(torch, t, name, dtype=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name}: expected a C-contiguous tensor")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+
+
+def stack_kernel_name(n, method="average", k_lo=5.0, k_hi=5.0, maxiters=1, cen="median",
+                      dev="mad_std", want_uncert=False, out_f64=False, force_generic=False):
+    lib = _native.load()
+    return lib.apgpu_stack_kernel_name(
+        int(n), METHODS[method], float(k_lo), float(k_hi), _maxiters(maxiters), CENFUNCS[cen],
+        DEVFUNCS[dev], int(want_uncert), int(out_f64), _FORCE_GENERIC if force_generic else 0).decode()
+
+
+def _maxiters(maxiters):
+    return -1 if maxiters is None else int(maxiters)
+
+
+def stack_reduce(frames, method="average", k_lo=5.0, k_hi=5.0, maxiters=1, cen="median",
+                 dev="mad_std", row0=0, nrows=None, out_f64=False, want_nrej=True,
+                 want_uncert=False, want_allmasked=False, force_generic=False, out=None):
+    """Per-pixel combine of N frames (``apgpu_stack_reduce_f32``).
+
+    ``frames``: a (N,H,W) float32 CUDA tensor or a sequence of N (H,W) float32
+    CUDA tensors.  Defaults are the reference's ApMasterCal settings
+    (scripts/ap_combine_darks.py:394-399): average after one 5-sigma
+    median/MAD clip.  Returns a dict of (H,W) tensors: ``data``, and when
+    requested ``nrej`` (uint8, or uint16 for N>255), ``uncert``, ``allmasked``.
+    Only rows ``[row0, row0+nrows)`` are written.
+    """
+    torch = _native.require_cuda()
+    lib = _native.load()
+    if isinstance(frames, torch.Tensor):
+        if frames.dim() != 3:
+            raise RuntimeError("stack_reduce: frame cube must be (N, H, W)")
+        _check_image(torch, frames, "frames", torch.float32)
+        flist = [frames[i] for i in range(frames.shape[0])]
+    else:
+        flist = list(frames)
+        for i, f in enumerate(flist):
+            _check_image(torch, f, f"frames[{i}]", torch.float32)
+    n = len(flist)
+    if n == 0:
+        raise RuntimeError("stack_reduce: no frames")
+    h, w = flist[0].shape
+    for f in flist:
+        if tuple(f.shape) != (h, w):
+            raise RuntimeError("stack_reduce: frames differ in shape")
+    if method not in METHODS or cen not in CENFUNCS or dev not in DEVFUNCS:
+        raise RuntimeError(f"stack_reduce: bad method/cen/dev {method}/{cen}/{dev}")
+    if nrows is None:
+        nrows = h - row0
+    device = flist[0].device
+    res = out if out is not None else {}
+    if "data" not in res:
+        res["data"] = torch.empty((h, w), dtype=torch.float64 if out_f64 else torch.float32, device=device)
+    if want_nrej and "nrej" not in res:
+        res["nrej"] = torch.empty((h, w), dtype=torch.uint8 if n <= 255 else torch.uint16, device=device)
+    if want_uncert and "uncert" not in res:
+        res["uncert"] = torch.empty_like(res["data"])
+    if want_allmasked and "allmasked" not in res:
+        res["allmasked"] = torch.empty((h, w), dtype=torch.uint8, device=device)
+    ptrs = (ctypes.c_void_p * n)(*[f.data_ptr() for f in flist])
+    nrej = res.get("nrej") if want_nrej else None
+    st = lib.apgpu_stack_reduce_f32(
+        ptrs, n, h, w, int(row0), int(nrows), METHODS[method], float(k_lo), float(k_hi),
+        _maxiters(maxiters), CENFUNCS[cen], DEVFUNCS[dev],
+        _ptr(res["data"]), int(res["data"].dtype == torch.float64),
+        _ptr(nrej), int(nrej is not None and nrej.dtype == torch.uint16),
+        _ptr(res.get("uncert") if want_uncert else None),
+        _ptr(res.get("allmasked") if want_allmasked else None),
+        _FORCE_GENERIC if force_generic else 0, _stream(torch))
+    _native.check(st, "apgpu_stack_reduce_f32")
+    return res
+
+
+def flat_norm(flat):
+    """``np.nanmean(flat)`` as a 1-element float32 CUDA tensor (bit-exact numpy tree)."""
+    torch = _native.require_cuda()
+    lib = _native.load()
+    _check_image(torch, flat, "flat", torch.float32)
+    npix = flat.numel()
+    nbytes = int(lib.apgpu_flat_norm_workspace_bytes(npix))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=flat.device)
+    norm = torch.empty(1, dtype=torch.float32, device=flat.device)
+    _native.check(lib.apgpu_flat_norm_f32(_ptr(flat), npix, _ptr(ws), nbytes, _ptr(norm), _stream(torch)),
+                  "apgpu_flat_norm_f32")
+    return norm
+
+
+def flat_normalise(flat, norm=None):
+    """``flat / np.nanmean(flat)`` (ApCalibrate._generate_flat, core/ApCalibrate.py:178-190)."""
+    torch = _native.require_cuda()
+    lib = _native.load()
+    if norm is None:
+        norm = flat_norm(flat)
+    out = torch.empty_like(flat)
+    _native.check(lib.apgpu_flat_divide_f32(_ptr(flat), _ptr(norm), _ptr(out), flat.numel(), _stream(torch)),
+                  "apgpu_flat_divide_f32")
+    return out, norm
+
+
+def calibrate(raw, bias, dark, normflat=None, exp_ratio=1.0, dark_still_biased=False,
+              pedestal=None, out=None):
+    """Fused bias / scaled-dark / flat calibration (core/ApCalibrate.py:439-474).
+
+    ``raw`` may be float32 (already converted, pedestal applied) or uint16
+    (conversion and optional ``pedestal`` fused into the kernel)."""
+    torch = _native.require_cuda()
+    lib = _native.load()
+    _check_image(torch, raw, "raw")
+    _check_image(torch, bias, "bias", torch.float32)
+    _check_image(torch, dark, "dark", torch.float32)
+    if normflat is not None:
+        _check_image(torch, normflat, "normflat", torch.float32)
+    for name, t in (("bias", bias), ("dark", dark), ("normflat", normflat)):
+        if t is not None and tuple(t.shape) != tuple(raw.shape):
+            raise RuntimeError(f"calibrate: {name} shape {tuple(t.shape)} != raw shape {tuple(raw.shape)}")
+    if out is None:
+        out = torch.empty(raw.shape, dtype=torch.float32, device=raw.device)
+    npix = raw.numel()
+    if raw.dtype == torch.float32:
+        if pedestal:
+            raise RuntimeError("calibrate: pedestal fusion is for uint16 raw frames only")
+        st = lib.apgpu_calibrate_f32(_ptr(raw), _ptr(bias), _ptr(dark), _ptr(normflat),
+                                     float(exp_ratio), int(bool(dark_still_biased)), _ptr(out), npix,
+                                     _stream(torch))
+    elif raw.dtype == torch.uint16:
+        has_ped = pedestal is not None and float(pedestal) != 0.0
+        st = lib.apgpu_calibrate_u16(_ptr(raw), float(pedestal or 0.0), int(has_ped), _ptr(bias),
+                                     _ptr(dark), _ptr(normflat), float(exp_ratio),
+                                     int(bool(dark_still_biased)), _ptr(out), npix, _stream(torch))
+    else:
+        raise RuntimeError(f"calibrate: raw dtype {raw.dtype} not supported (float32 or uint16)")
+    _native.check(st, "apgpu_calibrate")
+    return out
+
+
+_MASK_DTYPES = None
+
+
+def _mask_code(torch, dtype):
+    global _MASK_DTYPES
+    if _MASK_DTYPES is None:
+        _MASK_DTYPES = {torch.uint8: 0, torch.bool: 0, torch.int16: 1, torch.uint16: 1,
+                        torch.int32: 2, torch.float32: 3, torch.float64: 4}
+    if dtype not in _MASK_DTYPES:
+        raise RuntimeError(f"fix_badpix: mask dtype {dtype} not supported")
+    return _MASK_DTYPES[dtype]
+
+
+def fix_badpix(data, mask, deltapix=1, min_valid=4, image_rows=None, band_row0=0,
+               row0=None, nrows=None, counts=None):
+    """Median repair of masked pixels (core/ApFixBadPixels.py:380-419).
+
+    ``data``/``mask`` hold rows ``[band_row0, band_row0+data.shape[0])`` of an
+    image with ``image_rows`` rows (defaults: the whole image).  Returns
+    ``(out, counts)`` where ``out`` has ``nrows`` rows starting at image row
+    ``row0`` and ``counts`` is a 2-element int64 CUDA tensor
+    ``[n_bad, n_fixed]`` (accumulated into when passed in)."""
+    torch = _native.require_cuda()
+    lib = _native.load()
+    _check_image(torch, data, "data", torch.float32)
+    _check_image(torch, mask, "mask")
+    if tuple(data.shape) != tuple(mask.shape):
+        raise RuntimeError(f"Error, the shape of the input data array ({tuple(data.shape)}) does not "
+                           f"match that of the bad pixel mask array ({tuple(mask.shape)}).")
+    band_rows, w = data.shape
+    if image_rows is None:
+        image_rows = band_row0 + band_rows
+    if row0 is None:
+        row0 = band_row0
+    if nrows is None:
+        nrows = band_row0 + band_rows - row0
+    out = torch.empty((nrows, w), dtype=torch.float32, device=data.device)
+    if counts is None:
+        counts = torch.zeros(2, dtype=torch.int64, device=data.device)
+    st = lib.apgpu_fix_badpix_f32(_ptr(data), _ptr(mask), _mask_code(torch, mask.dtype),
+                                  int(image_rows), int(w), int(band_row0), int(band_rows),
+                                  int(row0), int(nrows), int(deltapix), int(min_valid),
+                                  _ptr(out), _ptr(counts), _stream(torch))
+    _native.check(st, "apgpu_fix_badpix_f32")
+    return out, counts
