@@ -28,7 +28,7 @@ NVCC_FLAGS = [
     "--fmad=false",                    # parity: numpy never fuses multiply-add; fmaf() where wanted
     "-Xcompiler", "-fPIC,-O2",
     "-Xptxas", "-v",
-    "-DAPGPU_BUILDING",
+    "-DAPGPU_BUILDING", *(["-DAPGPU_DEBUG_MEDMAD"] if os.environ.get("APGPU_DEBUG") else []),
 ]
 
 

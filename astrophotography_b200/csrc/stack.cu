@@ -213,6 +213,19 @@ stack_generic_kernel(const __grid_constant__ FramePtrs<CAP> fp, const __grid_con
 // elements carry a (warp-uniform) runtime predicate.
 #define APGPU_ACTIVE(i) ((i) < NLO || (i) < N)
 
+template <int K>
+__device__ __forceinline__ float tree_sum(const float (&v)[K]) {
+    float t[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) t[k] = v[k];
+#pragma unroll
+    for (int w = K / 2; w >= 1; w /= 2) {
+#pragma unroll
+        for (int k = 0; k < w; ++k) t[k] = t[2 * k] + t[2 * k + 1];
+    }
+    return t[0];
+}
+
 __device__ __forceinline__ float med3(float a, float b, float c) {
     return fmaxf(fminf(a, b), fminf(fmaxf(a, b), c));
 }
@@ -231,24 +244,28 @@ stack_meanclip_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_con
     // further float32 arithmetic is on y = x - pivot, which keeps the sums
     // small and the variance free of catastrophic cancellation.
     const float pivot = med3(y[0], y[1], y[2]);
+    // NACC interleaved float32 accumulators: ILP, and a summation error bound of
+    // (N/NACC + log2 NACC + 1) roundings instead of N.
+    constexpr int NACC = NB <= 64 ? 4 : (NB <= 128 ? 8 : 16);
     float z = 0.f;                       // NaN iff some sample is NaN/inf
-    float s1[4] = {0.f, 0.f, 0.f, 0.f};
-    float s2[4] = {0.f, 0.f, 0.f, 0.f};
+    float s1[NACC], s2[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
         if (APGPU_ACTIVE(i)) {
             z = fmaf(y[i], 0.f, z);
             float d = y[i] - pivot;
             y[i] = d;
-            s1[i & 3] += d;
-            s2[i & 3] = fmaf(d, d, s2[i & 3]);
+            s1[i % NACC] += d;
+            s2[i % NACC] = fmaf(d, d, s2[i % NACC]);
         }
     }
     if (z != z) { generic_pixel<NB>(fp, a, p); return; }
 
     int nk = N;
-    float S1 = (s1[0] + s1[1]) + (s1[2] + s1[3]);
-    float S2 = (s2[0] + s2[1]) + (s2[2] + s2[3]);
+    float S1 = tree_sum<NACC>(s1);
+    float S2 = tree_sum<NACC>(s2);
     const float klo = (float)a.klo, khi = (float)a.khi;
     const float kmax = fmaxf(klo, khi);
     bool uncertain = false;
@@ -264,13 +281,14 @@ stack_meanclip_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_con
         // Bound on |threshold_f32 - threshold_exact| + |y_f32 - y_exact|:
         // summation over 4 interleaved accumulators, unit roundoff doubled for safety.
         const float u2 = 1.1920929e-7f;                       // 2^-23
-        const float m = 0.25f * fn + 6.f;
+        const float m = fn / (float)NACC + 8.f;
         const float g = m * u2 * (sqrtf(ex2) + 1.5f * kmax * ex2 / sd) + 6.f * u2 * (fabsf(c) + kmax * sd);
         if (!(g < 0.25f * kmax * sd)) { uncertain = true; break; }   // degenerate (var ~ 0, NaN): let float64 decide
         const float lo_out = (c - klo * sd) - g, lo_in = (c - klo * sd) + g;
         const float hi_out = (c + khi * sd) + g, hi_in = (c + khi * sd) - g;
-        float n1[4] = {0.f, 0.f, 0.f, 0.f};
-        float n2[4] = {0.f, 0.f, 0.f, 0.f};
+        float n1[NACC], n2[NACC];
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) { n1[k] = 0.f; n2[k] = 0.f; }
         int kept = 0;
         bool unc = false;
 #pragma unroll
@@ -281,8 +299,8 @@ stack_meanclip_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_con
             unc |= (keep != sure);
             if (keep) {
                 ++kept;
-                n1[i & 3] += d;
-                n2[i & 3] = fmaf(d, d, n2[i & 3]);
+                n1[i % NACC] += d;
+                n2[i % NACC] = fmaf(d, d, n2[i % NACC]);
             } else {
                 y[i] = NAN;
             }
@@ -290,19 +308,34 @@ stack_meanclip_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_con
         if (unc) { uncertain = true; break; }
         const bool changed = kept != nk;
         nk = kept;
-        S1 = (n1[0] + n1[1]) + (n1[2] + n1[3]);
-        S2 = (n2[0] + n2[1]) + (n2[2] + n2[3]);
+        S1 = tree_sum<NACC>(n1);
+        S2 = tree_sum<NACC>(n2);
         if (!changed || nk == 0) break;
     }
     if (uncertain || nk == 0) { generic_pixel<NB>(fp, a, p); return; }
 
-    // mean of the survivors = pivot + S1/nk, evaluated in float64: S1 is a sum
-    // of small shifted values, so its float32 error is ~1e-9 of the result.
-    double mean = __dadd_rn((double)pivot, __ddiv_rn((double)S1, (double)nk));
+    // mean of the survivors = pivot + sum(y)/nk.  float32 output: the float32
+    // sums of the small shifted values are accurate to ~1e-8 of
+    // max(|mean|, sigma).  float64 output: the shifted values are summed in
+    // float64 (exact), which leaves only the rounding of y = x - pivot itself
+    // (none at all when x and pivot are within a factor 2, Sterbenz).
+    double sum1 = (double)S1, sum2 = (double)S2;
+    if (a.out_f64) {
+        sum1 = 0.0; sum2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            if (y[i] == y[i]) {
+                double d = (double)y[i];
+                sum1 = __dadd_rn(sum1, d);
+                sum2 = __dadd_rn(sum2, __dmul_rn(d, d));
+            }
+        }
+    }
+    const double cy = __ddiv_rn(sum1, (double)nk);
+    const double mean = __dadd_rn((double)pivot, cy);
     double unc_out = (double)NAN;
     if (a.uncert) {
-        double cy = __ddiv_rn((double)S1, (double)nk);
-        double var = __dsub_rn(__ddiv_rn((double)S2, (double)nk), __dmul_rn(cy, cy));
+        double var = __dsub_rn(__ddiv_rn(sum2, (double)nk), __dmul_rn(cy, cy));
         unc_out = __ddiv_rn(__dsqrt_rn(var > 0.0 ? var : 0.0), __dsqrt_rn((double)nk));
     }
     write_pixel(a, p, mean, N - nk, unc_out, 0);
@@ -327,7 +360,7 @@ APGPU_DEF_SORT(112) APGPU_DEF_SORT(128)
 template <int NB, int NLO, int MODE>
 __global__ void __launch_bounds__(TPB)
 stack_sorted_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_constant__ StackArgs a) {
-    extern __shared__ float col[];       // MODE_MEDMAD1: [NB][TPB] sorted columns
+    extern __shared__ float col[];       // MODE_MEDMAD1: [NB + 2][TPB] sorted columns + guard rows
     const int64_t p = a.pix0 + (int64_t)blockIdx.x * TPB + threadIdx.x;
     if (p >= a.pix0 + a.npix) return;
     const int N = a.N;
@@ -366,27 +399,31 @@ stack_sorted_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_const
         return;
     }
 
-    // Park the sorted column in shared memory ([i][thread]: conflict-free for
-    // any per-thread index) for the data-dependent selection below.
-    float* s = col + threadIdx.x;
+    // Park the sorted column in shared memory ([row][thread]: conflict-free for
+    // any per-thread row index) for the data-dependent selection below.  Row 0
+    // and row NB+1 are -inf / +inf guards, so together with the +-inf padding
+    // every row outside the real samples has an infinite deviation from the
+    // median and the merge below needs no bounds checks.
+    float* s = col + threadIdx.x + TPB;          // s[i * TPB] = sorted sample i, i in [-1, NB]
+    s[-TPB] = -INFINITY;
+    s[NB * TPB] = INFINITY;
 #pragma unroll
     for (int i = 0; i < NB; ++i) s[i * TPB] = x[i];
-    const int base = nneg;               // real samples occupy [base, base + N)
+    const int base = nneg;               // real samples occupy rows [base, base + N)
     // MAD by two-pointer merge outwards from the median (float64, exact).
     int l = base + ((N - 1) >> 1), r = l + 1;
     const int k1 = (N - 1) >> 1, k2 = N >> 1;
     double d1 = 0.0, d2 = 0.0;
     double dl = fabs(__dsub_rn((double)s[l * TPB], med));
-    double dr = (r < base + N) ? fabs(__dsub_rn((double)s[r * TPB], med)) : (double)INFINITY;
+    double dr = fabs(__dsub_rn((double)s[r * TPB], med));
     for (int t = 0; t <= k2; ++t) {
-        double d;
-        if (dl <= dr) {
-            d = dl; --l;
-            dl = (l >= base) ? fabs(__dsub_rn((double)s[l * TPB], med)) : (double)INFINITY;
-        } else {
-            d = dr; ++r;
-            dr = (r < base + N) ? fabs(__dsub_rn((double)s[r * TPB], med)) : (double)INFINITY;
-        }
+        const bool left = dl <= dr;
+        const double d = left ? dl : dr;
+        l -= left ? 1 : 0;
+        r += left ? 0 : 1;
+        const double dn = fabs(__dsub_rn((double)s[(left ? l : r) * TPB], med));
+        dl = left ? dn : dl;
+        dr = left ? dr : dn;
         if (t == k1) d1 = d;
         if (t == k2) d2 = d;
     }
@@ -398,6 +435,10 @@ stack_sorted_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_const
     while (sa < sb && (double)s[sa * TPB] < lo) ++sa;
     while (sa < sb && (double)s[(sb - 1) * TPB] > hi) --sb;
     const int nk = sb - sa;
+#ifdef APGPU_DEBUG_MEDMAD
+    if (p == a.pix0) printf("dbg N=%d NB=%d base=%d med=%.6f d1=%.6f d2=%.6f mad=%.6f lo=%.6f hi=%.6f sa=%d sb=%d klo=%f\n",
+        N, NB, base, med, d1, d2, mad, lo, hi, sa, sb, a.klo);
+#endif
     double mean;
     if (nk == N) {
         mean = __ddiv_rn(sum_all, (double)N);
@@ -480,7 +521,7 @@ int launch_sorted(const float* const* frames, const StackArgs& a, cudaStream_t s
     FramePtrs<NB> fp;
     for (int i = 0; i < NB; ++i) fp.p[i] = i < a.N ? frames[i] : nullptr;
     int64_t blocks = (a.npix + TPB - 1) / TPB;
-    size_t smem = (MODE == MODE_MEDMAD1) ? (size_t)NB * TPB * sizeof(float) : 0;
+    size_t smem = (MODE == MODE_MEDMAD1) ? (size_t)(NB + 2) * TPB * sizeof(float) : 0;
     if (smem > 48 * 1024)
         APGPU_CUDA(cudaFuncSetAttribute(stack_sorted_kernel<NB, NLO, MODE>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

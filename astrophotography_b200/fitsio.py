@@ -1,0 +1,314 @@
+"""FITS I/O seam.
+
+The reference keeps all file I/O in ``astropy.io.fits`` (every ``Ap*`` class has
+its own ``_read_fits`` / ``_write_corrected_image``, e.g.
+``core/ApCalibrate.py:260-328,348-404``); so does this package whenever astropy
+is importable.  astropy is not installable in the authoring container or on the
+GPU box (no network), so a small self-contained reader/writer for the subset
+the hot path needs -- 2-D image HDUs, BITPIX 8/16/32/-32/-64, the unsigned
+16-bit ``BZERO=32768`` convention (``uint=True``), image extensions -- stands in
+when it is absent.  Either way the rest of the package only sees
+``read_image`` / ``write_image`` / ``read_header`` and the small ``Header``
+mapping below; arithmetic never happens here.
+"""
+from __future__ import annotations
+
+import os
+from collections import OrderedDict
+
+import numpy as np
+
+try:                                    # pragma: no cover - not available offline
+    from astropy.io import fits as _afits
+    HAVE_ASTROPY = True
+except Exception:                       # noqa: BLE001
+    _afits = None
+    HAVE_ASTROPY = False
+
+BLOCK = 2880
+_BITPIX_DTYPE = {8: ">u1", 16: ">i2", 32: ">i4", 64: ">i8", -32: ">f4", -64: ">f8"}
+_STRUCTURAL = ("SIMPLE", "XTENSION", "BITPIX", "NAXIS", "NAXIS1", "NAXIS2", "NAXIS3", "EXTEND",
+               "PCOUNT", "GCOUNT", "BZERO", "BSCALE", "END")
+
+
+class _Comments:
+    def __init__(self, hdr):
+        self._hdr = hdr
+
+    def __getitem__(self, key):
+        return self._hdr._cards[key.upper()][1]
+
+
+class Header:
+    """Ordered keyword -> (value, comment) mapping with HISTORY lines; the
+    subset of ``astropy.io.fits.Header`` behaviour the Ap* classes rely on."""
+
+    def __init__(self, cards=None):
+        self._cards = OrderedDict()
+        self.history = []
+        if cards:
+            for k, v in (cards.items() if hasattr(cards, "items") else cards):
+                self[k] = v
+
+    def __contains__(self, key):
+        return str(key).upper() in self._cards
+
+    def __getitem__(self, key):
+        return self._cards[str(key).upper()][0]
+
+    def __setitem__(self, key, value):
+        key = str(key).upper()
+        if key == "HISTORY":
+            self.history.append(str(value))
+            return
+        if isinstance(value, tuple):
+            val, com = (value + ("",))[:2]
+        else:
+            val, com = value, self._cards.get(key, (None, ""))[1]
+        self._cards[key] = (val, com or "")
+
+    def __delitem__(self, key):
+        del self._cards[str(key).upper()]
+
+    def __iter__(self):
+        return iter(self._cards)
+
+    def __len__(self):
+        return len(self._cards)
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def keys(self):
+        return self._cards.keys()
+
+    def items(self):
+        return [(k, v[0]) for k, v in self._cards.items()]
+
+    @property
+    def comments(self):
+        return _Comments(self)
+
+    def copy(self):
+        h = Header()
+        h._cards = OrderedDict(self._cards)
+        h.history = list(self.history)
+        return h
+
+
+# ---------------------------------------------------------------------------
+# minimal reader
+# ---------------------------------------------------------------------------
+def _parse_value(raw):
+    raw = raw.strip()
+    if not raw:
+        return None
+    if raw.startswith("'"):
+        end = 1
+        out = []
+        while end < len(raw):
+            if raw[end] == "'":
+                if end + 1 < len(raw) and raw[end + 1] == "'":
+                    out.append("'")
+                    end += 2
+                    continue
+                break
+            out.append(raw[end])
+            end += 1
+        return "".join(out).rstrip()
+    if raw in ("T", "F"):
+        return raw == "T"
+    try:
+        return int(raw)
+    except ValueError:
+        pass
+    try:
+        return float(raw.replace("D", "E").replace("d", "e"))
+    except ValueError:
+        return raw
+
+
+def _split_value_comment(body):
+    """Split ``value / comment`` honouring quoted strings."""
+    inq = False
+    for i, ch in enumerate(body):
+        if ch == "'":
+            inq = not inq
+        elif ch == "/" and not inq:
+            return body[:i], body[i + 1:].strip()
+    return body, ""
+
+
+def _read_header_block(f):
+    hdr = Header()
+    while True:
+        block = f.read(BLOCK)
+        if len(block) < BLOCK:
+            raise OSError("truncated FITS header")
+        done = False
+        for i in range(0, BLOCK, 80):
+            card = block[i:i + 80].decode("ascii", "replace")
+            key = card[:8].strip()
+            if key == "END":
+                done = True
+                break
+            if key == "HISTORY":
+                hdr.history.append(card[8:].rstrip())
+            elif key and card[8:10] == "= ":
+                val, com = _split_value_comment(card[10:])
+                hdr._cards[key] = (_parse_value(val), com)
+        if done:
+            return hdr
+
+
+def _data_nbytes(hdr):
+    naxis = int(hdr.get("NAXIS", 0))
+    if naxis == 0:
+        return 0, ()
+    shape = tuple(int(hdr[f"NAXIS{i}"]) for i in range(naxis, 0, -1))
+    n = abs(int(hdr["BITPIX"])) // 8
+    for s in shape:
+        n *= s
+    return n, shape
+
+
+def _mini_read(path, ext, header_only=False):
+    with open(path, "rb") as f:
+        for hdu in range(ext + 1):
+            hdr = _read_header_block(f)
+            nbytes, shape = _data_nbytes(hdr)
+            padded = (nbytes + BLOCK - 1) // BLOCK * BLOCK
+            if hdu < ext:
+                f.seek(padded, os.SEEK_CUR)
+                continue
+            if header_only or nbytes == 0:
+                return None, hdr
+            raw = np.frombuffer(f.read(nbytes), dtype=_BITPIX_DTYPE[int(hdr["BITPIX"])]).reshape(shape)
+    bzero = hdr.get("BZERO", 0) or 0
+    bscale = hdr.get("BSCALE", 1) or 1
+    bitpix = int(hdr["BITPIX"])
+    if bitpix == 16 and bscale == 1 and bzero == 32768:          # uint=True convention
+        data = (raw.astype(np.int32) + 32768).astype(np.uint16)
+    elif bscale == 1 and bzero == 0:
+        data = raw.astype(raw.dtype.newbyteorder("="))
+    else:                                                        # generic scaling, as astropy does
+        data = (raw.astype(np.float32 if bitpix in (8, 16) else np.float64) * bscale + bzero)
+    return data, hdr
+
+
+# ---------------------------------------------------------------------------
+# minimal writer
+# ---------------------------------------------------------------------------
+def _fmt_value(val):
+    if isinstance(val, (bool, np.bool_)):
+        return f"{'T' if val else 'F':>20}"
+    if isinstance(val, (int, np.integer)):
+        return f"{int(val):>20d}"
+    if isinstance(val, (float, np.floating)):
+        s = repr(float(val)).upper()
+        if "E" not in s and "." not in s and "N" not in s:
+            s += ".0"
+        return f"{s:>20}"
+    s = str(val).replace("'", "''")
+    return f"'{s:<8}'"
+
+
+def _card(key, val, com=""):
+    body = f"{key:<8}= {_fmt_value(val)}"
+    if com:
+        body += f" / {com}"
+    return body[:80].ljust(80)
+
+
+def _encode_hdu(data, hdr, primary, extname=None):
+    cards = []
+    data = None if data is None else np.asarray(data)
+    bzero = None
+    if data is None:
+        bitpix, shape, payload = 8, (), b""
+    else:
+        if data.dtype == np.bool_:
+            data = data.astype(np.uint8)
+        if data.dtype == np.uint16:
+            bitpix, bzero = 16, 32768
+            payload = (data.astype(np.int32) - 32768).astype(">i2").tobytes()
+        else:
+            code = {"u1": 8, "i2": 16, "i4": 32, "i8": 64, "f4": -32, "f8": -64}.get(data.dtype.str[1:])
+            if code is None:
+                raise TypeError(f"cannot write dtype {data.dtype} to FITS")
+            bitpix = code
+            payload = data.astype(data.dtype.newbyteorder(">")).tobytes()
+        shape = data.shape
+    cards.append(_card("SIMPLE", True, "conforms to FITS standard") if primary
+                 else _card("XTENSION", "IMAGE", "Image extension"))
+    cards.append(_card("BITPIX", bitpix, "array data type"))
+    cards.append(_card("NAXIS", len(shape), "number of array dimensions"))
+    for i, s in enumerate(reversed(shape)):
+        cards.append(_card(f"NAXIS{i + 1}", s))
+    if primary:
+        cards.append(_card("EXTEND", True))
+    else:
+        cards.append(_card("PCOUNT", 0))
+        cards.append(_card("GCOUNT", 1))
+        if extname:
+            cards.append(_card("EXTNAME", extname, "extension name"))
+    if bzero is not None:
+        cards.append(_card("BSCALE", 1))
+        cards.append(_card("BZERO", bzero))
+    if hdr is not None:
+        for key in hdr.keys():
+            if key in _STRUCTURAL or (not primary and key == "EXTNAME"):
+                continue
+            cards.append(_card(key, hdr[key], hdr.comments[key]))
+        for line in getattr(hdr, "history", []):
+            cards.append(("HISTORY " + str(line))[:80].ljust(80))
+    cards.append("END".ljust(80))
+    head = "".join(cards).encode("ascii", "replace")
+    head += b" " * (-len(head) % BLOCK)
+    payload += b"\0" * (-len(payload) % BLOCK)
+    return head + payload
+
+
+# ---------------------------------------------------------------------------
+# public seam
+# ---------------------------------------------------------------------------
+def read_image(path, ext=0):
+    """Return ``(data, header)`` of image HDU ``ext`` (``uint=True`` semantics:
+    BITPIX 16 with BZERO 32768 comes back as uint16)."""
+    if HAVE_ASTROPY:                    # pragma: no cover
+        with _afits.open(path, uint=True, do_not_scale_image_data=False) as hl:
+            return np.asarray(hl[ext].data), hl[ext].header.copy()
+    return _mini_read(str(path), ext)
+
+
+def read_header(path, ext=0):
+    if HAVE_ASTROPY:                    # pragma: no cover
+        return _afits.getheader(path, ext)
+    return _mini_read(str(path), ext, header_only=True)[1]
+
+
+def new_header(cards=None):
+    if HAVE_ASTROPY:                    # pragma: no cover
+        h = _afits.Header()
+        for k, v in (cards or {}).items():
+            h[k] = v
+        return h
+    return Header(cards)
+
+
+def write_image(path, data, header=None, extensions=(), overwrite=True):
+    """Write a primary image HDU plus optional ``(extname, data)`` image extensions."""
+    path = str(path)
+    if os.path.exists(path) and not overwrite:
+        raise OSError(f"{path} exists")
+    if HAVE_ASTROPY:                    # pragma: no cover
+        hdus = [_afits.PrimaryHDU(data=data, header=header)]
+        for name, d in extensions:
+            hdus.append(_afits.ImageHDU(data=d, name=name))
+        _afits.HDUList(hdus).writeto(path, output_verify="ignore", overwrite=True)
+        return
+    blob = _encode_hdu(data, header, True)
+    for name, d in extensions:
+        blob += _encode_hdu(d, None, False, extname=name)
+    with open(path, "wb") as f:
+        f.write(blob)

@@ -1,0 +1,394 @@
+#!/usr/bin/env python3
+"""Benchmark of the FITS-reduction hot path on B200 (see BASELINE.json / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--small]
+
+Headline (``value``): Mpix-frames/s of the kappa-sigma-clipped mean stack
+(kappa=3, <=5 iterations, BASELINE.json config 3's algorithm) over
+100 x (9576 x 6388) float32 frames resident in HBM -- the workload BASELINE.json's
+target is quoted on.  One step = one pass of the stack reducer over the whole
+cube (24.5 GB, far larger than the 126 MB L2, so no L2 flush is needed between
+steps).  ``e2e`` is the same metric through the host-buffer API
+(``HostStackCombiner``): frames in pinned host memory, H2D + kernel + D2H of the
+result inside the timed region.  ``roofline`` is for the stack kernel
+(algorithmic bytes 4*N+5 per pixel over the CUDA-event kernel time, against the
+measured copy bandwidth in MEASURED_PEAKS.json).  ``cpu_baseline`` times the
+numpy oracle port of the same algorithm on a bounded row sample on the host.
+``variants`` reports the other kernels of the path (the reference's own
+ApMasterCal median/MAD setting, plain median, calibrate, bad-pixel repair).
+
+Multi-GPU (torchrun, one process per GPU): weak scaling -- every rank reduces
+its own 100 x (9576 x 6388) row band of a taller mosaic; no data-path collective
+(SURVEY.md section 8e); barrier + max-over-ranks timing.
+
+``--impl reference``: the reference's CPU implementation of the same workload
+(the numpy oracle port of ccdproc.combine / astropy.sigma_clip -- the reference
+itself is numpy-based and ccdproc/astropy cannot be installed here), all host
+threads, each step a bounded row sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HEADLINE = dict(method="average", k_lo=3.0, k_hi=3.0, maxiters=5, cen="mean", dev="std")
+FULL = dict(n=100, h=6388, w=9576)          # 100 x (9576 x 6388): W=9576 columns, H=6388 rows
+SMALL = dict(n=100, h=512, w=2048)          # --small: quick functional run
+METRIC = "Mpix-frames/sec sigma-clip stack (kappa=3, 5 iters) of 100x(9576x6388) f32; % HBM roofline"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------
+# synthetic data, generated on the device for the big cube
+# ---------------------------------------------------------------------------
+def synth_cube_device(torch, n, h, w, device, seed):
+    """N dark-like frames: 1000 + N(0,12) + fixed hot pixels + per-frame cosmic hits."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    cube = torch.empty((n, h, w), dtype=torch.float32, device=device)
+    nhot = int(round(5e-4 * h * w))
+    hot_idx = torch.randint(0, h * w, (nhot,), generator=g, device=device)
+    hot_amp = 5000.0 * (0.5 + 0.5 * torch.rand(nhot, generator=g, device=device))
+    ncos = int(round(1e-4 * h * w))
+    for k in range(n):
+        f = cube[k]
+        f.normal_(1000.0, 12.0, generator=g)
+        f.view(-1).index_add_(0, hot_idx, hot_amp)
+        cidx = torch.randint(0, h * w, (ncos,), generator=g, device=device)
+        camp = 500.0 + 29500.0 * torch.rand(ncos, generator=g, device=device)
+        f.view(-1).index_add_(0, cidx, camp)
+    return cube
+
+
+def synth_cube_host(n, h, w, seed):
+    rng = np.random.default_rng(seed)
+    cube = rng.normal(1000.0, 12.0, size=(n, h, w)).astype(np.float32)
+    nhot = int(round(5e-4 * h * w))
+    hot = rng.integers(0, h * w, nhot)
+    cube.reshape(n, -1)[:, hot] += (5000.0 * rng.uniform(0.5, 1.0, nhot)).astype(np.float32)
+    ncos = int(round(1e-4 * h * w))
+    for k in range(n):
+        ci = rng.integers(0, h * w, ncos)
+        cube[k].reshape(-1)[ci] += rng.uniform(500, 30000, ncos).astype(np.float32)
+    return cube
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:            # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------
+# reference arm / cpu baseline (oracle port on host cores)
+# ---------------------------------------------------------------------------
+def cpu_combine_rows(cube_rows, params, threads):
+    """Oracle port on a (N, rows, W) host sample, split over ``threads`` row bands."""
+    from oracle import combine_oracle as C
+    rows = cube_rows.shape[1]
+    if threads <= 1:
+        C.combine(cube_rows, want_uncert=False, **params)
+        return
+    from concurrent.futures import ThreadPoolExecutor
+    bounds = np.linspace(0, rows, threads + 1).astype(int)
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(lambda i: C.combine(cube_rows[:, bounds[i]:bounds[i + 1]], want_uncert=False, **params),
+                    [i for i in range(threads) if bounds[i + 1] > bounds[i]]))
+
+
+def run_reference(args, shape):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n, h, w = shape["n"], shape["h"], shape["w"]
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    rows = min(h, max(cores, 4 * cores))           # bounded sample: a few seconds per step
+    cube = synth_cube_host(n, rows, w, seed=1000)
+    for _ in range(args.warmup):
+        cpu_combine_rows(cube, HEADLINE, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_combine_rows(cube, HEADLINE, cores)
+    dt = time.perf_counter() - t0
+    mpf = n * rows * w / 1e6
+    value = mpf * args.steps / dt
+    sample = f"{n} frames x {rows} rows x {w} cols per step ({mpf:.1f} Mpix-frames), numpy oracle port, {cores} threads over row bands"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpix-frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": workload_name(shape), **{k: v for k, v in HEADLINE.items()}, "l2": "inputs >> L2"},
+        "cpu_baseline": {"value": value, "unit": "Mpix-frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Mpix-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_name(shape):
+    return f"kappa-sigma-clipped mean stack {shape['n']}x({shape['w']}x{shape['h']}) float32"
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def time_steps(torch, fn, steps, warmup, dist=None):
+    """CUDA-event timing on the current stream; barrier + sync on both sides; max over ranks."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        fn()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.barrier()
+        ms = float(t.item())
+    return ms
+
+
+def run_gpu(args, shape):
+    import torch
+    from astrophotography_b200 import _native, kernels, pipeline, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    device = torch.device("cuda", local_rank)
+    n, h, w = shape["n"], shape["h"], shape["w"]
+    mpix = h * w / 1e6
+    hbm_peak, peak_src = peaks()
+
+    cube = synth_cube_device(torch, n, h, w, device, seed=1000 + rank)
+    out = {"data": torch.empty((h, w), dtype=torch.float32, device=device),
+           "nrej": torch.empty((h, w), dtype=torch.uint8, device=device)}
+    torch.cuda.synchronize()
+
+    def step():
+        kernels.stack_reduce(cube, out=out, **HEADLINE)
+
+    sampler = ClockSampler(local_rank)
+    launches0 = _native.launch_count()
+    sampler.start()
+    ms = time_steps(torch, step, args.steps, args.warmup, dist)
+    clocks = sampler.stop()
+    launches = (_native.launch_count() - launches0) * args.steps // (args.steps + args.warmup)
+    ms_per_step = ms / args.steps
+    value = world * n * mpix / (ms_per_step * 1e-3)
+    alg_bytes = (4 * n + 5) * h * w
+    achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+    kname = kernels.stack_kernel_name(n, **HEADLINE)
+
+    # ---- other kernels of the path (rank 0 reporting only; short runs) ----
+    variants = {}
+
+    def add_variant(name, fn, units_mpix, nbytes, steps=3, unit="Mpix-frames/s"):
+        vms = time_steps(torch, fn, steps, 2) / steps
+        variants[name] = {"value": units_mpix / (vms * 1e-3), "unit": unit, "ms": vms,
+                          "hbm_gbs": nbytes / (vms * 1e-3) / 1e9,
+                          "frac_of_peak": nbytes / (vms * 1e-3) / 1e9 / hbm_peak}
+
+    if not args.no_variants:
+        ref = dict(method="average", k_lo=5.0, k_hi=5.0, maxiters=1, cen="median", dev="mad_std")
+        add_variant("stack_medmad_5sigma_1pass_apmastercal[%s]" % kernels.stack_kernel_name(n, **ref),
+                    lambda: kernels.stack_reduce(cube, out=out, **ref), n * mpix, alg_bytes)
+        med = dict(method="median", maxiters=0)
+        add_variant("stack_median[%s]" % kernels.stack_kernel_name(n, **med),
+                    lambda: kernels.stack_reduce(cube, out=out, want_nrej=False, **med), n * mpix, (4 * n + 4) * h * w)
+        c30 = cube[:30]
+        add_variant("stack_kappa_sigma_N30[%s]" % kernels.stack_kernel_name(30, **HEADLINE),
+                    lambda: kernels.stack_reduce(c30, out=out, **HEADLINE), 30 * mpix, (4 * 30 + 5) * h * w)
+        raw = torch.randint(0, 65535, (h, w), dtype=torch.int32, device=device).to(torch.int16).view(torch.uint16)
+        bias, dark = cube[0], cube[1]
+        flat = (30000.0 * (1 + 0.01 * torch.randn((h, w), device=device))).contiguous()
+        nflat, _ = kernels.flat_normalise(flat)
+        cal = torch.empty((h, w), dtype=torch.float32, device=device)
+        add_variant("calibrate_u16_fused", lambda: kernels.calibrate(raw, bias, dark, nflat, 1.0 / 3.0, True, out=cal),
+                    mpix, 18 * h * w, steps=5, unit="Mpix/s")
+        rawf = cube[2]
+        add_variant("calibrate_f32_fused", lambda: kernels.calibrate(rawf, bias, dark, nflat, 1.0 / 3.0, True, out=cal),
+                    mpix, 20 * h * w, steps=5, unit="Mpix/s")
+        mask = torch.from_numpy(synth.badpix_mask((h, w), auto_fraction=1e-3)).to(device)
+        add_variant("fix_badpix_dp2", lambda: kernels.fix_badpix(cal, mask, 2), mpix, 9 * h * w, steps=5, unit="Mpix/s")
+        add_variant("flat_norm_nanmean", lambda: kernels.flat_norm(flat), mpix, 4 * h * w, steps=5, unit="Mpix/s")
+        del raw, flat, nflat, cal, mask
+
+    # ---- end to end through the host-buffer API (pinned host frames) ----
+    e2e = None
+    if not args.no_e2e:
+        avail = _mem_available_bytes()
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+        need = n * h * w * 4
+        n_host = n
+        if avail is not None and need * local_world > 0.55 * avail:
+            n_host = max(4, int(0.55 * avail / local_world / (h * w * 4)))
+        host_frames, keep = [], []
+        for i in range(min(n, n_host)):
+            arr, t = pipeline.pinned_empty((h, w), np.float32)
+            t.copy_(cube[i])
+            host_frames.append(arr)
+            keep.append(t)
+        torch.cuda.synchronize()
+        frames = [host_frames[i % len(host_frames)] for i in range(n)]
+        comb = pipeline.HostStackCombiner(n, h, w, **HEADLINE, band_bytes=2 << 30, device=device)
+        esteps = max(1, min(args.steps, 3))
+        comb.combine(frames)                                     # warm-up
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(esteps):
+            res = comb.combine(frames)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        # check the e2e result against the device-resident result
+        same = bool(np.array_equal(res["data"], out["data"].cpu().numpy(), equal_nan=True)) if n_host == n else None
+        e2e = {"value": world * n * mpix * esteps / dt, "unit": "Mpix-frames/s",
+               "h2d_bytes_per_step": comb.h2d_bytes, "d2h_bytes_per_step": comb.d2h_bytes,
+               "steps": esteps, "ms_per_step": 1e3 * dt / esteps, "api": "pipeline.HostStackCombiner.combine",
+               "host_frames_distinct": len(host_frames), "matches_device_path": same,
+               "pcie_gbs": comb.h2d_bytes * esteps / dt / 1e9}
+        del comb, keep, host_frames, frames
+
+    # ---- CPU baseline: oracle port, single thread, bounded sample (rank 0, N=1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        rows = min(h, 96)
+        sample = cube[:, :rows].cpu().numpy()
+        t0 = time.perf_counter()
+        cpu_combine_rows(sample, HEADLINE, 1)
+        dt = time.perf_counter() - t0
+        cpu = {"value": n * rows * w / 1e6 / dt, "unit": "Mpix-frames/s", "cores": 1, "kind": "port",
+               "sample": f"{n} frames x {rows} rows x {w} cols ({n * rows * w / 1e6:.1f} Mpix-frames) of the same cube, "
+                         f"numpy oracle port (oracle/combine_oracle.py), 1 thread, {dt:.1f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "Mpix-frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(shape), **HEADLINE, "kernel": kname,
+                       "per_gpu": f"{n}x({w}x{h})", "l2": "inputs (24.5 GB/GPU) >> L2 (126 MB): no flush needed"},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel": kname},
+            "e2e": e2e, "cpu_baseline": cpu, "variants": variants,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def _mem_available_bytes():
+    try:
+        with open("/proc/meminfo") as f:
+            for ln in f:
+                if ln.startswith("MemAvailable:"):
+                    return int(ln.split()[1]) * 1024
+    except OSError:
+        pass
+    return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--small", action="store_true", help="small cube (functional check, not a valid bench number)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-variants", action="store_true")
+    args = ap.parse_args()
+    shape = SMALL if args.small else FULL
+    if args.impl == "reference":
+        run_reference(args, shape)
+    else:
+        run_gpu(args, shape)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,240 @@
+"""GPU parity: frame-stack reducer vs the float64 numpy oracle (oracle/combine_oracle.py).
+
+Bars: median/min/max selection bit-exact; clipped means
+within 1e-6 relative in float32 (the generic kernel and every float64 output
+are checked far tighter); rejection-count maps identical.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import bits_equal
+
+pytestmark = pytest.mark.gpu
+
+RTOL32 = 1e-6          # north_star tolerance for float32 clipped means
+
+
+def _stack(n, shape, seed=0, quantise=False, specials=True):
+    rng = np.random.default_rng(seed * 1000 + n)
+    h, w = shape
+    st = rng.normal(1000.0, 12.0, size=(n, h, w)).astype(np.float32)
+    hits = rng.random((n, h, w)) < 0.004                       # cosmic-ray-like outliers
+    st[hits] += rng.uniform(500, 30000, size=int(hits.sum())).astype(np.float32)
+    st[:, 0, : min(w, 6)] += 4000.0                            # hot pixels: high in every frame
+    if quantise:
+        st = np.rint(st).astype(np.float32)
+    if specials and h * w > 40:
+        st[0, 1, 1] = np.nan
+        st[n // 2, 1, 2] = np.inf
+        st[n - 1, 1, 3] = -np.inf
+        st[:, 1, 4] = np.nan                                   # an all-NaN pixel
+        st[:, 1, 5] = 7.0                                      # all samples equal
+        st[: n // 2, 1, 6] = 5.0                               # two values only
+        st[n // 2:, 1, 6] = 6.0
+    return st
+
+
+def _run(torch, st, **kw):
+    from astrophotography_b200 import kernels
+    cube = torch.from_numpy(np.ascontiguousarray(st)).cuda()
+    res = kernels.stack_reduce(cube, want_nrej=True, want_allmasked=True, **kw)
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy() for k, v in res.items()}
+
+
+def _oracle(st, method, k_lo, k_hi, maxiters, cen, dev):
+    from oracle import combine_oracle as C
+    return C.combine(st, method, k_lo, k_hi, maxiters, cen, dev)
+
+
+def _assert_close_data(got, exp, rtol, scale):
+    both_nan = np.isnan(got) & np.isnan(exp)
+    with np.errstate(invalid="ignore"):
+        same_inf = np.isinf(exp) & (got == exp)
+        ok = both_nan | same_inf | (np.abs(got - exp) <= rtol * np.maximum(np.abs(exp), scale))
+    assert ok.all(), (np.argwhere(~ok)[:5], got[~ok][:5], exp[~ok][:5])
+
+
+def test_kat_hand_computed(cuda, golden_dir):
+    """The hand-derived known-answer stacks (tests/golden/combine_kat.npz)."""
+    torch = cuda
+    k = np.load(os.path.join(golden_dir, "combine_kat.npz"))
+    def close(got, exp, force, skip=()):
+        # The generic kernel is the oracle's arithmetic (1e-15).  The fast kernels promise
+        # 1e-6 of max(|mean|, spread): KAT pixel B[3] = [1e30, -1e30, 1, 2] is ill-conditioned
+        # by design and is only checked on the generic path.
+        keep = np.ones(exp.shape, bool)
+        if not force:
+            keep[list(skip)] = False
+        return np.allclose(got[keep], exp[keep], rtol=1e-15 if force else 1e-6, atol=0, equal_nan=True)
+
+    for force in (False, True):
+        a = _run(torch, k["A_stack"], method="average", k_lo=5, k_hi=5, maxiters=1, cen="median",
+                 dev="mad_std", out_f64=True, want_uncert=True, force_generic=force)
+        assert close(a["data"][0], k["A_mean"], force)
+        assert np.array_equal(a["nrej"][0], k["A_nrej"])
+        assert np.array_equal(a["allmasked"][0], k["A_allmasked"])
+        assert np.allclose(a["uncert"][0], k["A_uncert"], rtol=1e-15, atol=0, equal_nan=True)
+        for m, key in (("median", "B_median"), ("min", "B_min"), ("max", "B_max"), ("average", "B_mean")):
+            b = _run(torch, k["B_stack"], method=m, maxiters=0, out_f64=True, force_generic=force)
+            assert close(b["data"][0], k[key], force, skip=(3,) if m == "average" else ()), (m, b["data"][0])
+            assert np.array_equal(b["nrej"][0], k["B_nrej"])
+        c = _run(torch, k["C_stack"], method="average", k_lo=1.5, k_hi=1.5, maxiters=5, cen="mean",
+                 dev="std", out_f64=True, force_generic=force)
+        assert close(c["data"][0], k["C_mean"], force) and np.array_equal(c["nrej"][0], k["C_nrej"])
+        d = _run(torch, k["D_stack"], method="average", k_lo=0.2, k_hi=3.0, maxiters=1, cen="median",
+                 dev="std", out_f64=True, force_generic=force)
+        assert close(d["data"][0], k["D_mean"], force) and np.array_equal(d["nrej"][0], k["D_nrej"])
+
+
+GENERIC_CASES = [
+    # method, k_lo, k_hi, maxiters, cen, dev
+    ("average", 5.0, 5.0, 1, "median", "mad_std"),     # ApMasterCal (ap_combine_darks.py:394-399)
+    ("average", 3.0, 3.0, 5, "median", "std"),         # astropy.stats.sigma_clip defaults
+    ("average", 3.0, 3.0, 5, "mean", "std"),           # kappa-sigma, BASELINE config 3
+    ("average", 2.5, 4.0, None, "mean", "mad_std"),    # asymmetric, to convergence
+    ("median", 3.0, 3.0, 2, "median", "mad_std"),
+    ("median", 5.0, 5.0, 0, "median", "mad_std"),      # plain median
+    ("average", 5.0, 5.0, 0, "median", "mad_std"),     # plain mean
+    ("min", 3.0, 3.0, 1, "mean", "std"),
+    ("max", 3.0, 3.0, 0, "mean", "std"),
+]
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 10, 31, 100, 130])
+@pytest.mark.parametrize("case", GENERIC_CASES, ids=lambda c: "-".join(map(str, c)))
+def test_generic_kernel_bit_exact_f64(cuda, n, case):
+    """The generic kernel is the oracle's arithmetic in its operation order: float64
+    outputs must be bit-identical, rejection maps identical, on every parameter set."""
+    torch = cuda
+    method, k_lo, k_hi, maxiters, cen, dev = case
+    st = _stack(n, (12, 40), seed=1, quantise=(n % 2 == 0))
+    exp = _oracle(st, method, k_lo, k_hi, maxiters, cen, dev)
+    got = _run(torch, st, method=method, k_lo=k_lo, k_hi=k_hi, maxiters=maxiters, cen=cen, dev=dev,
+               out_f64=True, want_uncert=True, force_generic=True)
+    assert np.array_equal(got["nrej"].astype(np.int64), exp["nrej"])
+    assert np.array_equal(got["allmasked"], exp["allmasked"])
+    assert bits_equal(got["data"], exp["data"])
+    if not (maxiters == 0 and not np.isfinite(st).all()):
+        assert bits_equal(got["uncert"], exp["uncert"])
+
+
+FAST_CASES = [
+    ("average", 5.0, 5.0, 1, "median", "mad_std", "sorted_medmad1"),
+    ("average", 3.0, 3.0, 1, "median", "mad_std", "sorted_medmad1"),
+    ("median", 5.0, 5.0, 0, "median", "mad_std", "sorted_median"),
+    ("average", 3.0, 3.0, 5, "mean", "std", "meanclip"),
+    ("average", 2.0, 3.5, None, "mean", "std", "meanclip"),
+    ("average", 3.0, 3.0, 1, "mean", "std", "meanclip"),
+    ("average", 3.0, 3.0, 0, "mean", "std", "meanclip"),
+]
+
+
+@pytest.mark.parametrize("n", [3, 4, 5, 8, 9, 16, 17, 24, 30, 33, 50, 64, 65, 81, 90, 99, 100, 101, 113, 128])
+@pytest.mark.parametrize("case", FAST_CASES, ids=lambda c: "-".join(map(str, c)))
+@pytest.mark.parametrize("quantise", [False, True])
+def test_fast_kernels_match_oracle(cuda, n, case, quantise):
+    torch = cuda
+    from astrophotography_b200 import kernels
+    method, k_lo, k_hi, maxiters, cen, dev, family = case
+    name = kernels.stack_kernel_name(n, method, k_lo, k_hi, maxiters, cen, dev)
+    assert name.startswith(family), name
+    st = _stack(n, (9, 70), seed=2, quantise=quantise)
+    exp = _oracle(st, method, k_lo, k_hi, maxiters, cen, dev)
+    for out_f64 in (False, True):
+        got = _run(torch, st, method=method, k_lo=k_lo, k_hi=k_hi, maxiters=maxiters, cen=cen, dev=dev,
+                   out_f64=out_f64)
+        assert np.array_equal(got["nrej"].astype(np.int64), exp["nrej"]), (name, out_f64)
+        assert np.array_equal(got["allmasked"], exp["allmasked"])
+        if family == "sorted_median":
+            # selection is comparison-only: exact (the even-N midpoint of two float32 is exact in float64)
+            e = exp["data"] if out_f64 else exp["data"].astype(np.float32)
+            assert bits_equal(got["data"], e)
+        else:
+            # float64 output: the sorted kernel sums in float64 (<= a few ulp of the oracle);
+            # the meanclip kernel sums pivot-shifted float32 values exactly in float64.
+            rt = RTOL32 if not out_f64 else (1e-13 if family.startswith("sorted") else 2e-7)
+            _assert_close_data(got["data"].astype(np.float64), exp["data"], rt, 12.0)
+
+
+@pytest.mark.parametrize("n", [130, 160, 200])
+def test_meanclip_large_n(cuda, n):
+    torch = cuda
+    from astrophotography_b200 import kernels
+    assert kernels.stack_kernel_name(n, "average", 3, 3, 5, "mean", "std").startswith("meanclip")
+    st = _stack(n, (6, 64), seed=4)
+    exp = _oracle(st, "average", 3.0, 3.0, 5, "mean", "std")
+    got = _run(torch, st, method="average", k_lo=3.0, k_hi=3.0, maxiters=5, cen="mean", dev="std", want_uncert=True)
+    assert np.array_equal(got["nrej"].astype(np.int64), exp["nrej"])
+    _assert_close_data(got["data"].astype(np.float64), exp["data"], RTOL32, 1.0)
+    _assert_close_data(got["uncert"].astype(np.float64), exp["uncert"], 1e-5, 1e-3)
+
+
+def test_fast_uncert(cuda):
+    torch = cuda
+    st = _stack(30, (8, 64), seed=5)
+    exp = _oracle(st, "average", 5.0, 5.0, 1, "median", "mad_std")
+    got = _run(torch, st, method="average", out_f64=True, want_uncert=True)
+    assert np.array_equal(got["nrej"].astype(np.int64), exp["nrej"])
+    _assert_close_data(got["uncert"], exp["uncert"], 1e-12, 1e-6)
+    _assert_close_data(got["data"], exp["data"], 1e-13, 1.0)
+
+
+def test_unclipped_pixels_mean_is_bit_exact(cuda):
+    """Where nothing is rejected the sorted kernel sums in frame order like np.nanmean."""
+    torch = cuda
+    rng = np.random.default_rng(8)
+    st = rng.normal(1000, 10, size=(30, 16, 64)).astype(np.float32)
+    exp = _oracle(st, "average", 5.0, 5.0, 1, "median", "mad_std")
+    got = _run(torch, st, method="average", out_f64=True)
+    keep_all = exp["nrej"] == 0
+    assert keep_all.mean() > 0.9
+    assert np.array_equal(got["data"][keep_all], exp["data"][keep_all])
+
+
+def test_row_band_only_touches_its_rows(cuda):
+    torch = cuda
+    from astrophotography_b200 import kernels
+    st = _stack(10, (32, 48), seed=6, specials=False)
+    exp = _oracle(st, "average", 5.0, 5.0, 1, "median", "mad_std")
+    cube = torch.from_numpy(st).cuda()
+    out = {"data": torch.full((32, 48), -1.0, device="cuda"),
+           "nrej": torch.full((32, 48), 255, dtype=torch.uint8, device="cuda")}
+    kernels.stack_reduce(cube, row0=5, nrows=11, out=out)
+    d = out["data"].cpu().numpy()
+    assert (d[:5] == -1).all() and (d[16:] == -1).all()
+    _assert_close_data(d[5:16].astype(np.float64), exp["data"][5:16], RTOL32, 1.0)
+    assert (out["nrej"].cpu().numpy()[16:] == 255).all()
+
+
+def test_separate_frame_pointers_and_u16_counts(cuda):
+    """Frames as N separate allocations (the reference stacks N files) and N > 255."""
+    torch = cuda
+    from astrophotography_b200 import kernels
+    n = 260
+    st = _stack(n, (4, 33), seed=7, specials=False)
+    frames = [torch.from_numpy(st[i].copy()).cuda() for i in range(n)]
+    res = kernels.stack_reduce(frames, method="average", k_lo=3, k_hi=3, maxiters=3, cen="median", dev="std",
+                               out_f64=True)
+    assert res["nrej"].dtype == torch.uint16
+    exp = _oracle(st, "average", 3.0, 3.0, 3, "median", "std")
+    assert np.array_equal(res["nrej"].cpu().numpy().astype(np.int64), exp["nrej"])
+    assert bits_equal(res["data"].cpu().numpy(), exp["data"])
+
+
+def test_stack_errors(cuda):
+    torch = cuda
+    from astrophotography_b200 import kernels
+    a = torch.zeros((3, 4, 4), device="cuda")
+    with pytest.raises(RuntimeError):
+        kernels.stack_reduce(a.to(torch.float64))
+    with pytest.raises(RuntimeError):
+        kernels.stack_reduce([a[0], a[1, :2]])
+    with pytest.raises(RuntimeError):
+        kernels.stack_reduce(a, method="mode")
+    with pytest.raises(RuntimeError, match="geometry"):
+        kernels.stack_reduce(a, row0=3, nrows=2)
+    with pytest.raises(RuntimeError):
+        kernels.stack_reduce(torch.zeros((0, 4, 4), device="cuda"))
