@@ -230,42 +230,57 @@ __device__ __forceinline__ float med3(float a, float b, float c) {
     return fmaxf(fminf(a, b), fminf(fmaxf(a, b), c));
 }
 
-template <int NB, int NLO>
-__global__ void __launch_bounds__(TPB)
+// Sweep design (see DESIGN.md "meanclip"): the samples stay in registers as
+// y = x - pivot; a rejected sample is overwritten with 0 (it then adds nothing
+// to the running sums) and remembered in a bit mask.  A sweep walks the samples
+// in groups of G: the common path per sample is one subtract, one |t| max, and
+// the two sum updates (no predicates, no selects); only a group whose largest
+// |y - c| reaches the inner clip bound takes a branch into per-sample handling.
+template <int NB, int NLO, bool SYM>
+__global__ void __launch_bounds__(TPB, (NB <= 32 ? 6 : (NB <= 48 ? 5 : (NB <= 100 ? 4 : (NB <= 128 ? 3 : 2)))))
 stack_meanclip_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_constant__ StackArgs a) {
     const int64_t p = a.pix0 + (int64_t)blockIdx.x * TPB + threadIdx.x;
     if (p >= a.pix0 + a.npix) return;
     const int N = a.N;
+    constexpr int G = NB <= 160 ? 5 : 8;               // samples per group (at most 64 groups)
+    constexpr int NG = (NB + G - 1) / G;
+    constexpr int NW = (NB + 31) / 32;
     float y[NB];
 #pragma unroll
-    for (int i = 0; i < NB; ++i) y[i] = APGPU_ACTIVE(i) ? ld_stream(fp.p[i] + p) : NAN;
+    for (int i = 0; i < NB; ++i) y[i] = APGPU_ACTIVE(i) ? ld_stream(fp.p[i] + p) : 0.f;
 
     // Pivot: median of the first three frames (robust to one outlier).  All
-    // further float32 arithmetic is on y = x - pivot, which keeps the sums
-    // small and the variance free of catastrophic cancellation.
+    // float32 arithmetic below is on y = x - pivot: sums stay small and the
+    // variance is free of catastrophic cancellation.
     const float pivot = med3(y[0], y[1], y[2]);
-    // NACC interleaved float32 accumulators: ILP, and a summation error bound of
-    // (N/NACC + log2 NACC + 1) roundings instead of N.
-    constexpr int NACC = NB <= 64 ? 4 : (NB <= 128 ? 8 : 16);
-    float z = 0.f;                       // NaN iff some sample is NaN/inf
-    float s1[NACC], s2[NACC];
+    uint32_t rej[NW];                                  // bit i set: sample i is not (or no longer) used
 #pragma unroll
-    for (int k = 0; k < NACC; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
-#pragma unroll
-    for (int i = 0; i < NB; ++i) {
-        if (APGPU_ACTIVE(i)) {
-            z = fmaf(y[i], 0.f, z);
-            float d = y[i] - pivot;
-            y[i] = d;
-            s1[i % NACC] += d;
-            s2[i % NACC] = fmaf(d, d, s2[i % NACC]);
-        }
+    for (int wd = 0; wd < NW; ++wd) {
+        const int lo_i = wd * 32;
+        rej[wd] = (N >= lo_i + 32) ? 0u : (N <= lo_i ? 0xffffffffu : (0xffffffffu << (N - lo_i)));
     }
-    if (z != z) { generic_pixel<NB>(fp, a, p); return; }
+    float S1 = 0.f, S2 = 0.f;
+#pragma unroll
+    for (int gidx = 0; gidx < NG; ++gidx) {
+        float g1 = 0.f, g2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+            const int i = gidx * G + k;
+            if (i < NB) {
+                const float d = APGPU_ACTIVE(i) ? y[i] - pivot : 0.f;
+                y[i] = d;
+                g1 += d;
+                g2 = fmaf(d, d, g2);
+            }
+        }
+        S1 += g1;
+        S2 += g2;
+    }
+    // NaN input poisons S1/S2, inf input (or overflow) makes S2 infinite: the
+    // generic routine owns those semantics.
+    if (!(S2 <= FLT_MAX) || !(fabsf(S1) <= FLT_MAX)) { generic_pixel<NB>(fp, a, p); return; }
 
     int nk = N;
-    float S1 = tree_sum<NACC>(s1);
-    float S2 = tree_sum<NACC>(s2);
     const float klo = (float)a.klo, khi = (float)a.khi;
     const float kmax = fmaxf(klo, khi);
     bool uncertain = false;
@@ -278,57 +293,99 @@ stack_meanclip_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_con
         const float ex2 = S2 / fn;
         const float var = ex2 - c * c;
         const float sd = sqrtf(fmaxf(var, 0.f));
-        // Bound on |threshold_f32 - threshold_exact| + |y_f32 - y_exact| (see DESIGN.md):
-        // summation over 4 interleaved accumulators, unit roundoff doubled for safety.
+        // Bound on |threshold_f32 - threshold_exact| + |y_f32 - y_exact| (DESIGN.md):
+        // group-wise summation (G + NG terms deep), unit roundoff doubled for safety.
         const float u2 = 1.1920929e-7f;                       // 2^-23
-        const float m = fn / (float)NACC + 8.f;
+        const float m = (float)(G + NG + 8);
         const float g = m * u2 * (sqrtf(ex2) + 1.5f * kmax * ex2 / sd) + 6.f * u2 * (fabsf(c) + kmax * sd);
-        if (!(g < 0.25f * kmax * sd)) { uncertain = true; break; }   // degenerate (var ~ 0, NaN): let float64 decide
-        const float lo_out = (c - klo * sd) - g, lo_in = (c - klo * sd) + g;
-        const float hi_out = (c + khi * sd) + g, hi_in = (c + khi * sd) - g;
-        float n1[NACC], n2[NACC];
+        if (!(g < 0.25f * kmax * sd)) { uncertain = true; break; }   // degenerate (var ~ 0): let float64 decide
+        // inner (certainly kept inside) and outer (certainly rejected outside) bounds on t = y - c
+        const float lo_in = -klo * sd + g, lo_out = -klo * sd - g;
+        const float hi_in = khi * sd - g, hi_out = khi * sd + g;
+        const float t_in = fminf(-lo_in, hi_in);              // symmetric inner bound on |t|
+        const float ylo_out = c + lo_out, ylo_in = c + lo_in, yhi_in = c + hi_in, yhi_out = c + hi_out;
+        const int nk_before = nk;
+        float n1 = 0.f, n2 = 0.f;
+        uint64_t flags = 0;              // bit g: group g holds a sample outside the inner bounds
+        // common pass: tight straight-line code, no per-sample predicates
 #pragma unroll
-        for (int k = 0; k < NACC; ++k) { n1[k] = 0.f; n2[k] = 0.f; }
-        int kept = 0;
-        bool unc = false;
+        for (int gidx = 0; gidx < NG; ++gidx) {
+            float g1 = 0.f, g2 = 0.f, tmax = 0.f, tmin = 0.f;
 #pragma unroll
-        for (int i = 0; i < NB; ++i) {
-            const float d = y[i];
-            const bool keep = (d >= lo_out) && (d <= hi_out);     // NaN (already rejected / padding) fails
-            const bool sure = (d > lo_in) && (d < hi_in);
-            unc |= (keep != sure);
-            if (keep) {
-                ++kept;
-                n1[i % NACC] += d;
-                n2[i % NACC] = fmaf(d, d, n2[i % NACC]);
+            for (int k = 0; k < G; ++k) {
+                const int i = gidx * G + k;
+                if (i < NB) {
+                    const float t = y[i] - c;
+                    if (SYM) {
+                        tmax = fmaxf(tmax, fabsf(t));
+                    } else {
+                        tmax = fmaxf(tmax, t);
+                        tmin = fminf(tmin, t);
+                    }
+                    g1 += y[i];
+                    g2 = fmaf(y[i], y[i], g2);
+                }
+            }
+            const bool flagged = SYM ? (tmax >= t_in) : (tmax >= hi_in || tmin <= lo_in);
+            if (flagged) {
+                flags |= (uint64_t)1 << gidx;
             } else {
-                y[i] = NAN;
+                n1 += g1;
+                n2 += g2;
             }
         }
-        if (unc) { uncertain = true; break; }
-        const bool changed = kept != nk;
-        nk = kept;
-        S1 = tree_sum<NACC>(n1);
-        S2 = tree_sum<NACC>(n2);
-        if (!changed || nk == 0) break;
+        // rare pass: only the flagged groups, sample by sample
+        if (flags) {
+#pragma unroll
+            for (int gidx = 0; gidx < NG; ++gidx) {
+                if ((flags >> gidx) & 1) {
+                    float g1 = 0.f, g2 = 0.f;
+#pragma unroll
+                    for (int k = 0; k < G; ++k) {
+                        const int i = gidx * G + k;
+                        if (i < NB) {
+                            // compare y against bounds shifted by c (not t = y - c: keeps the
+                            // compiler from holding every t of the common pass live in registers)
+                            const float v = y[i];
+                            if (v < ylo_out || v > yhi_out) {        // certainly rejected
+                                y[i] = 0.f;                          // (idempotent for an already rejected sample)
+                                rej[i >> 5] |= 1u << (i & 31);
+                            } else if (!(v > ylo_in && v < yhi_in)) {
+                                uncertain = true;                    // inside the guard band: float64 must decide
+                            }
+                            g1 += y[i];
+                            g2 = fmaf(y[i], y[i], g2);
+                        }
+                    }
+                    n1 += g1;
+                    n2 += g2;
+                }
+            }
+            int nrej = 0;
+#pragma unroll
+            for (int wd = 0; wd < NW; ++wd) nrej += __popc(rej[wd]);
+            nk = NW * 32 - nrej;         // bits [N, NW*32) were set at init, so this is N - rejected
+        }
+        if (uncertain) break;
+        S1 = n1;
+        S2 = n2;
+        if (nk == nk_before || nk == 0) break;
     }
     if (uncertain || nk == 0) { generic_pixel<NB>(fp, a, p); return; }
 
-    // mean of the survivors = pivot + sum(y)/nk.  float32 output: the float32
-    // sums of the small shifted values are accurate to ~1e-8 of
-    // max(|mean|, sigma).  float64 output: the shifted values are summed in
-    // float64 (exact), which leaves only the rounding of y = x - pivot itself
-    // (none at all when x and pivot are within a factor 2, Sterbenz).
+    // mean of the survivors = pivot + sum(y)/nk (rejected samples are zeros).
+    // float32 output: the float32 sums of the small shifted values are accurate
+    // to ~1e-8 of max(|mean|, sigma).  float64 output: the shifted values are
+    // summed in float64 (exact), leaving only the rounding of y = x - pivot
+    // itself (none when x and pivot are within a factor 2, Sterbenz).
     double sum1 = (double)S1, sum2 = (double)S2;
     if (a.out_f64) {
         sum1 = 0.0; sum2 = 0.0;
 #pragma unroll
         for (int i = 0; i < NB; ++i) {
-            if (y[i] == y[i]) {
-                double d = (double)y[i];
-                sum1 = __dadd_rn(sum1, d);
-                sum2 = __dadd_rn(sum2, __dmul_rn(d, d));
-            }
+            const double d = (double)y[i];
+            sum1 = __dadd_rn(sum1, d);
+            sum2 = __dadd_rn(sum2, __dmul_rn(d, d));
         }
     }
     const double cy = __ddiv_rn(sum1, (double)nk);
@@ -511,7 +568,10 @@ int launch_meanclip(const float* const* frames, const StackArgs& a, cudaStream_t
     FramePtrs<NB> fp;
     for (int i = 0; i < NB; ++i) fp.p[i] = i < a.N ? frames[i] : nullptr;
     int64_t blocks = (a.npix + TPB - 1) / TPB;
-    stack_meanclip_kernel<NB, NLO><<<(unsigned)blocks, TPB, 0, st>>>(fp, a);
+    if ((float)a.klo == (float)a.khi)
+        stack_meanclip_kernel<NB, NLO, true><<<(unsigned)blocks, TPB, 0, st>>>(fp, a);
+    else
+        stack_meanclip_kernel<NB, NLO, false><<<(unsigned)blocks, TPB, 0, st>>>(fp, a);
     APGPU_LAUNCH_CHECK("stack_meanclip_kernel");
     return APGPU_OK;
 }

@@ -1,0 +1,52 @@
+#!/usr/bin/env python3
+"""Summarise an .ncu-rep (raw page) into the handful of metrics the roofline discussion needs.
+
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep [--md]
+"""
+import csv
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum", "launch__registers_per_thread", "launch__occupancy_limit_registers",
+    "launch__grid_size", "launch__block_size",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes_read.sum.per_second",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
+    "smsp__warps_eligible.avg.per_cycle_active",
+    "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
+    "smsp__sass_inst_executed_op_local_ld.sum", "smsp__sass_inst_executed_op_local_st.sum",
+]
+STALL = "smsp__average_warps_issue_stalled_"
+
+
+def main():
+    rep = sys.argv[1]
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    for r in rows[2:]:
+        d = dict(zip(hdr, r))
+        u = dict(zip(hdr, units))
+        print(f"## {d.get('Kernel Name', '?')[:110]}")
+        for k in KEYS:
+            if k in d and d[k] != "":
+                print(f"{k:75s} {d[k]:>16s} {u[k]}")
+        stalls = sorted(((float(v), k[len(STALL):].replace('_per_issue_active.ratio', ''))
+                         for k, v in d.items() if k.startswith(STALL) and k.endswith("_per_issue_active.ratio") and v),
+                        reverse=True)
+        print("stall reasons (warps per issue-active cycle): " +
+              ", ".join(f"{n}={v:.2f}" for v, n in stalls[:8]))
+        print()
+
+
+if __name__ == "__main__":
+    main()
