@@ -231,50 +231,55 @@ __device__ __forceinline__ float med3(float a, float b, float c) {
 }
 
 // Sweep design (see DESIGN.md "meanclip"): the samples stay in registers as
-// y = x - pivot; a rejected sample is overwritten with 0 (it then adds nothing
-// to the running sums) and remembered in a bit mask.  A sweep walks the samples
-// in groups of G: the common path per sample is one subtract, one |t| max, and
-// the two sum updates (no predicates, no selects); only a group whose largest
-// |y - c| reaches the inner clip bound takes a branch into per-sample handling.
+// y = x - pivot, two per 64-bit register pair so that the Blackwell packed
+// FADD2 / FFMA2 instructions update two samples per issue slot.  A rejected
+// sample is overwritten with 0 (it then adds nothing to the running sums).  A
+// sweep walks the samples in groups of 8: the common path per group is 4 FADD2
+// (t = y - c), 4 FADD2 + 4 FFMA2 (sums), the |t| maximum, one compare -- no
+// per-sample predicates or selects.  Only a group whose largest |y - c| reaches
+// the inner clip bound is revisited, sample by sample, in a second "rare" pass.
 template <int NB, int NLO, bool SYM>
 __global__ void __launch_bounds__(TPB, (NB <= 32 ? 6 : (NB <= 48 ? 5 : (NB <= 100 ? 4 : (NB <= 128 ? 3 : 2)))))
 stack_meanclip_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_constant__ StackArgs a) {
+    static_assert(NB % 2 == 0, "meanclip buckets must be even");
     const int64_t p = a.pix0 + (int64_t)blockIdx.x * TPB + threadIdx.x;
     if (p >= a.pix0 + a.npix) return;
     const int N = a.N;
-    constexpr int G = NB <= 160 ? 5 : 8;               // samples per group (at most 64 groups)
-    constexpr int NG = (NB + G - 1) / G;
-    constexpr int NW = (NB + 31) / 32;
-    float y[NB];
+    constexpr int NP = NB / 2;                         // register pairs
+    constexpr int GP = 4;                              // pairs (8 samples) per group
+    constexpr int NG = (NP + GP - 1) / GP;
+    static_assert(NG <= 64, "flag word too small");
+    const uint32_t p32 = (uint32_t)p;                  // host guarantees H*W < 2^32
+    float2 y[NP];
 #pragma unroll
-    for (int i = 0; i < NB; ++i) y[i] = APGPU_ACTIVE(i) ? ld_stream(fp.p[i] + p) : 0.f;
+    for (int j = 0; j < NP; ++j) {
+        y[j].x = APGPU_ACTIVE(2 * j) ? ld_stream(fp.p[2 * j] + p32) : 0.f;
+        y[j].y = APGPU_ACTIVE(2 * j + 1) ? ld_stream(fp.p[2 * j + 1] + p32) : 0.f;
+    }
 
     // Pivot: median of the first three frames (robust to one outlier).  All
     // float32 arithmetic below is on y = x - pivot: sums stay small and the
     // variance is free of catastrophic cancellation.
-    const float pivot = med3(y[0], y[1], y[2]);
-    uint32_t rej[NW];                                  // bit i set: sample i is not (or no longer) used
-#pragma unroll
-    for (int wd = 0; wd < NW; ++wd) {
-        const int lo_i = wd * 32;
-        rej[wd] = (N >= lo_i + 32) ? 0u : (N <= lo_i ? 0xffffffffu : (0xffffffffu << (N - lo_i)));
-    }
+    const float pivot = med3(y[0].x, y[0].y, y[1].x);
+    const float2 negpiv = make_float2(-pivot, -pivot);
     float S1 = 0.f, S2 = 0.f;
 #pragma unroll
     for (int gidx = 0; gidx < NG; ++gidx) {
-        float g1 = 0.f, g2 = 0.f;
+        float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int k = 0; k < G; ++k) {
-            const int i = gidx * G + k;
-            if (i < NB) {
-                const float d = APGPU_ACTIVE(i) ? y[i] - pivot : 0.f;
-                y[i] = d;
-                g1 += d;
-                g2 = fmaf(d, d, g2);
+        for (int k = 0; k < GP; ++k) {
+            const int j = gidx * GP + k;
+            if (j < NP) {
+                float2 d = __fadd2_rn(y[j], negpiv);
+                if (!APGPU_ACTIVE(2 * j)) d.x = 0.f;       // padding beyond N (compile-time false below NLO)
+                if (!APGPU_ACTIVE(2 * j + 1)) d.y = 0.f;
+                y[j] = d;
+                s1 = __fadd2_rn(s1, d);
+                s2 = __ffma2_rn(d, d, s2);
             }
         }
-        S1 += g1;
-        S2 += g2;
+        S1 += s1.x + s1.y;
+        S2 += s2.x + s2.y;
     }
     // NaN input poisons S1/S2, inf input (or overflow) makes S2 infinite: the
     // generic routine owns those semantics.
@@ -294,9 +299,9 @@ stack_meanclip_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_con
         const float var = ex2 - c * c;
         const float sd = sqrtf(fmaxf(var, 0.f));
         // Bound on |threshold_f32 - threshold_exact| + |y_f32 - y_exact|:
-        // group-wise summation (G + NG terms deep), unit roundoff doubled for safety.
+        // group-wise summation (GP + 1 + NG terms deep), unit roundoff doubled for safety.
         const float u2 = 1.1920929e-7f;                       // 2^-23
-        const float m = (float)(G + NG + 8);
+        const float m = (float)(GP + NG + 9);
         const float g = m * u2 * (sqrtf(ex2) + 1.5f * kmax * ex2 / sd) + 6.f * u2 * (fabsf(c) + kmax * sd);
         if (!(g < 0.25f * kmax * sd)) { uncertain = true; break; }   // degenerate (var ~ 0): let float64 decide
         // inner (certainly kept inside) and outer (certainly rejected outside) bounds on t = y - c
@@ -304,34 +309,39 @@ stack_meanclip_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_con
         const float hi_in = khi * sd - g, hi_out = khi * sd + g;
         const float t_in = fminf(-lo_in, hi_in);              // symmetric inner bound on |t|
         const float ylo_out = c + lo_out, ylo_in = c + lo_in, yhi_in = c + hi_in, yhi_out = c + hi_out;
+        // A rejected sample is overwritten with y = 0 (the pivot), so the pivot itself must sit
+        // strictly inside the inner bounds: then zeros are never rejected (again) and add nothing.
+        if (!(ylo_in < 0.f && yhi_in > 0.f)) { uncertain = true; break; }
+        const float2 negc = make_float2(-c, -c);
         const int nk_before = nk;
         float n1 = 0.f, n2 = 0.f;
         uint64_t flags = 0;              // bit g: group g holds a sample outside the inner bounds
         // common pass: tight straight-line code, no per-sample predicates
 #pragma unroll
         for (int gidx = 0; gidx < NG; ++gidx) {
-            float g1 = 0.f, g2 = 0.f, tmax = 0.f, tmin = 0.f;
+            float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
+            float tmax = 0.f, tmin = 0.f;
 #pragma unroll
-            for (int k = 0; k < G; ++k) {
-                const int i = gidx * G + k;
-                if (i < NB) {
-                    const float t = y[i] - c;
+            for (int k = 0; k < GP; ++k) {
+                const int j = gidx * GP + k;
+                if (j < NP) {
+                    const float2 t = __fadd2_rn(y[j], negc);
                     if (SYM) {
-                        tmax = fmaxf(tmax, fabsf(t));
+                        tmax = fmaxf(tmax, fmaxf(fabsf(t.x), fabsf(t.y)));
                     } else {
-                        tmax = fmaxf(tmax, t);
-                        tmin = fminf(tmin, t);
+                        tmax = fmaxf(tmax, fmaxf(t.x, t.y));
+                        tmin = fminf(tmin, fminf(t.x, t.y));
                     }
-                    g1 += y[i];
-                    g2 = fmaf(y[i], y[i], g2);
+                    s1 = __fadd2_rn(s1, y[j]);
+                    s2 = __ffma2_rn(y[j], y[j], s2);
                 }
             }
             const bool flagged = SYM ? (tmax >= t_in) : (tmax >= hi_in || tmin <= lo_in);
             if (flagged) {
                 flags |= (uint64_t)1 << gidx;
             } else {
-                n1 += g1;
-                n2 += g2;
+                n1 += s1.x + s1.y;
+                n2 += s2.x + s2.y;
             }
         }
         // rare pass: only the flagged groups, sample by sample
@@ -339,32 +349,30 @@ stack_meanclip_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_con
 #pragma unroll
             for (int gidx = 0; gidx < NG; ++gidx) {
                 if ((flags >> gidx) & 1) {
-                    float g1 = 0.f, g2 = 0.f;
+                    float g1 = 0.f, g2 = 0.f, vmax = 0.f, vmin = 0.f;
 #pragma unroll
-                    for (int k = 0; k < G; ++k) {
-                        const int i = gidx * G + k;
+                    for (int k = 0; k < 2 * GP; ++k) {
+                        const int i = gidx * 2 * GP + k;
                         if (i < NB) {
                             // compare y against bounds shifted by c (not t = y - c: keeps the
                             // compiler from holding every t of the common pass live in registers)
-                            const float v = y[i];
-                            if (v < ylo_out || v > yhi_out) {        // certainly rejected
-                                y[i] = 0.f;                          // (idempotent for an already rejected sample)
-                                rej[i >> 5] |= 1u << (i & 31);
-                            } else if (!(v > ylo_in && v < yhi_in)) {
-                                uncertain = true;                    // inside the guard band: float64 must decide
-                            }
-                            g1 += y[i];
-                            g2 = fmaf(y[i], y[i], g2);
+                            float v = (i & 1) ? y[i >> 1].y : y[i >> 1].x;
+                            const bool keep = (v >= ylo_out) && (v <= yhi_out);
+                            nk -= keep ? 0 : 1;                      // certainly rejected
+                            v = keep ? v : 0.f;
+                            if (i & 1) y[i >> 1].y = v; else y[i >> 1].x = v;
+                            vmax = fmaxf(vmax, v);
+                            vmin = fminf(vmin, v);
+                            g1 += v;
+                            g2 = fmaf(v, v, g2);
                         }
                     }
+                    // a survivor inside the guard band: float64 must decide
+                    if (!(vmin > ylo_in && vmax < yhi_in)) uncertain = true;
                     n1 += g1;
                     n2 += g2;
                 }
             }
-            int nrej = 0;
-#pragma unroll
-            for (int wd = 0; wd < NW; ++wd) nrej += __popc(rej[wd]);
-            nk = NW * 32 - nrej;         // bits [N, NW*32) were set at init, so this is N - rejected
         }
         if (uncertain) break;
         S1 = n1;
@@ -382,10 +390,158 @@ stack_meanclip_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_con
     if (a.out_f64) {
         sum1 = 0.0; sum2 = 0.0;
 #pragma unroll
-        for (int i = 0; i < NB; ++i) {
-            const double d = (double)y[i];
-            sum1 = __dadd_rn(sum1, d);
-            sum2 = __dadd_rn(sum2, __dmul_rn(d, d));
+        for (int j = 0; j < NP; ++j) {
+            const double d0 = (double)y[j].x, d1 = (double)y[j].y;
+            sum1 = __dadd_rn(__dadd_rn(sum1, d0), d1);
+            sum2 = __dadd_rn(__dadd_rn(sum2, __dmul_rn(d0, d0)), __dmul_rn(d1, d1));
+        }
+    }
+    const double cy = __ddiv_rn(sum1, (double)nk);
+    const double mean = __dadd_rn((double)pivot, cy);
+    double unc_out = (double)NAN;
+    if (a.uncert) {
+        double var = __dsub_rn(__ddiv_rn(sum2, (double)nk), __dmul_rn(cy, cy));
+        unc_out = __ddiv_rn(__dsqrt_rn(var > 0.0 ? var : 0.0), __dsqrt_rn((double)nk));
+    }
+    write_pixel(a, p, mean, N - nk, unc_out, 0);
+}
+
+// ---------------------------------------------------------------------------
+// meanclip_smem<SYM, CAP>: the same algorithm with the pixel's samples parked in
+// shared memory instead of registers, any N that fits (N <= ~450).
+// ---------------------------------------------------------------------------
+// Each thread owns one pixel and one shared-memory column of float4 groups
+// ([group][thread] layout: 128-bit accesses, conflict-free).  Because shared
+// memory can be indexed dynamically, every pass is a real loop: the code is a
+// few hundred instructions whatever N is (the register kernels unroll N-fold
+// and become instruction-fetch bound beyond ~64 frames), registers stay low,
+// and N is a run-time value.  Sweeps follow the meanclip design above: groups
+// of 8 samples, branch only when a group's largest |y - c| reaches the inner
+// bound.
+constexpr int SM_U = 4;      // float4 groups (16 frames) loaded per unrolled step of the load loop
+
+template <bool SYM, int CAP>
+__global__ void __launch_bounds__(TPB)
+stack_meanclip_smem_kernel(const __grid_constant__ FramePtrs<CAP> fp, const __grid_constant__ StackArgs a) {
+    extern __shared__ float4 tile4[];                  // [n4e][TPB]
+    const int64_t p = a.pix0 + (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (p >= a.pix0 + a.npix) return;
+    const uint32_t p32 = (uint32_t)p;
+    const int N = a.N;
+    const int n4 = (N + 3) >> 2;
+    const int n4e = (n4 + 1) & ~1;                     // even number of groups: sweeps take two per step
+    float4* col = tile4 + threadIdx.x;                 // col[g * TPB] = samples 4g .. 4g+3 of this pixel
+
+    const float pivot = med3(ld_stream(fp.p[0] + p32), ld_stream(fp.p[1] + p32), ld_stream(fp.p[2] + p32));
+    float S1 = 0.f, S2 = 0.f;
+    for (int g0 = 0; g0 < n4e; g0 += SM_U) {
+        float4 v[SM_U];
+#pragma unroll
+        for (int u = 0; u < SM_U; ++u) {
+            const int i = 4 * (g0 + u);
+            // samples beyond N are padded with the pivot: y = 0, which adds nothing anywhere
+            v[u].x = (i + 0 < N) ? ld_stream(fp.p[i + 0] + p32) : pivot;
+            v[u].y = (i + 1 < N) ? ld_stream(fp.p[i + 1] + p32) : pivot;
+            v[u].z = (i + 2 < N) ? ld_stream(fp.p[i + 2] + p32) : pivot;
+            v[u].w = (i + 3 < N) ? ld_stream(fp.p[i + 3] + p32) : pivot;
+        }
+#pragma unroll
+        for (int u = 0; u < SM_U; ++u) {
+            if (g0 + u < n4e) {
+                float4 y;
+                y.x = v[u].x - pivot; y.y = v[u].y - pivot; y.z = v[u].z - pivot; y.w = v[u].w - pivot;
+                const float g1 = (y.x + y.y) + (y.z + y.w);
+                const float g2 = fmaf(y.w, y.w, fmaf(y.z, y.z, fmaf(y.y, y.y, y.x * y.x)));
+                S1 += g1;
+                S2 += g2;
+                col[(g0 + u) * TPB] = y;
+            }
+        }
+    }
+    if (!(S2 <= FLT_MAX) || !(fabsf(S1) <= FLT_MAX)) { generic_pixel<CAP>(fp, a, p); return; }
+
+    int nk = N;
+    const float klo = (float)a.klo, khi = (float)a.khi;
+    const float kmax = fmaxf(klo, khi);
+    bool uncertain = false;
+    int it = 0;
+    while (a.maxiters != 0 && (a.maxiters < 0 || it < a.maxiters)) {
+        ++it;
+        if (S2 == 0.f) break;
+        const float fn = (float)nk;
+        const float c = S1 / fn;
+        const float ex2 = S2 / fn;
+        const float var = ex2 - c * c;
+        const float sd = sqrtf(fmaxf(var, 0.f));
+        const float u2 = 1.1920929e-7f;                       // 2^-23
+        const float m = (float)(n4 + 12);                     // group-wise summation depth, doubled roundoff
+        const float g = m * u2 * (sqrtf(ex2) + 1.5f * kmax * ex2 / sd) + 6.f * u2 * (fabsf(c) + kmax * sd);
+        if (!(g < 0.25f * kmax * sd)) { uncertain = true; break; }
+        const float lo_in = -klo * sd + g, lo_out = -klo * sd - g;
+        const float hi_in = khi * sd - g, hi_out = khi * sd + g;
+        const float t_in = fminf(-lo_in, hi_in);
+        const float ylo_out = c + lo_out, ylo_in = c + lo_in, yhi_in = c + hi_in, yhi_out = c + hi_out;
+        if (!(ylo_in < 0.f && yhi_in > 0.f)) { uncertain = true; break; }   // zeros (rejected/padding) must stay inside
+        const int nk_before = nk;
+        float n1 = 0.f, n2 = 0.f;
+        for (int gq = 0; gq < n4e; gq += 2) {
+            float4 q0 = col[gq * TPB], q1 = col[(gq + 1) * TPB];
+            float yv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+            float g1 = 0.f, g2 = 0.f, tmax = 0.f, tmin = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float t = yv[k] - c;
+                if (SYM) {
+                    tmax = fmaxf(tmax, fabsf(t));
+                } else {
+                    tmax = fmaxf(tmax, t);
+                    tmin = fminf(tmin, t);
+                }
+                g1 += yv[k];
+                g2 = fmaf(yv[k], yv[k], g2);
+            }
+            const bool flagged = SYM ? (tmax >= t_in) : (tmax >= hi_in || tmin <= lo_in);
+            if (flagged) {
+                g1 = 0.f; g2 = 0.f;
+                float vmax = 0.f, vmin = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    float v = yv[k];
+                    const bool keep = (v >= ylo_out) && (v <= yhi_out);
+                    nk -= keep ? 0 : 1;
+                    v = keep ? v : 0.f;
+                    yv[k] = v;
+                    vmax = fmaxf(vmax, v);
+                    vmin = fminf(vmin, v);
+                    g1 += v;
+                    g2 = fmaf(v, v, g2);
+                }
+                if (!(vmin > ylo_in && vmax < yhi_in)) uncertain = true;
+                col[gq * TPB] = make_float4(yv[0], yv[1], yv[2], yv[3]);
+                col[(gq + 1) * TPB] = make_float4(yv[4], yv[5], yv[6], yv[7]);
+            }
+            n1 += g1;
+            n2 += g2;
+        }
+        if (uncertain) break;
+        S1 = n1;
+        S2 = n2;
+        if (nk == nk_before || nk == 0) break;
+    }
+    if (uncertain || nk == 0) { generic_pixel<CAP>(fp, a, p); return; }
+
+    double sum1 = (double)S1, sum2 = (double)S2;
+    if (a.out_f64) {
+        sum1 = 0.0; sum2 = 0.0;
+        for (int gq = 0; gq < n4e; ++gq) {
+            const float4 q = col[gq * TPB];
+            const float yv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double d = (double)yv[k];
+                sum1 = __dadd_rn(sum1, d);
+                sum2 = __dadd_rn(sum2, __dmul_rn(d, d));
+            }
         }
     }
     const double cy = __ddiv_rn(sum1, (double)nk);
@@ -426,13 +582,14 @@ stack_sorted_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_const
     // (and NB/2 for even N) whatever N is.
     const int npad = NB - N;
     const int nneg = npad >> 1;          // -inf pads; the other npad-nneg are +inf
+    const uint32_t p32 = (uint32_t)p;    // host guarantees H*W < 2^32: one IMAD.WIDE per address
     float x[NB];
     float z = 0.f;
     double sum_all = 0.0;
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
         if (APGPU_ACTIVE(i)) {
-            x[i] = ld_stream(fp.p[i] + p);
+            x[i] = ld_stream(fp.p[i] + p32);
         } else {
             x[i] = (i - N < nneg) ? -INFINITY : INFINITY;
         }
@@ -519,7 +676,11 @@ stack_sorted_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_const
 // ---------------------------------------------------------------------------
 // host dispatch
 // ---------------------------------------------------------------------------
-enum Family { FAM_GENERIC = 0, FAM_MEANCLIP = 1, FAM_SORT_MED = 2, FAM_SORT_MEDMAD1 = 3 };
+enum Family { FAM_GENERIC = 0, FAM_MEANCLIP = 1, FAM_SORT_MED = 2, FAM_SORT_MEDMAD1 = 3, FAM_MEANCLIP_SMEM = 4 };
+
+constexpr int SMEM_MAX_BYTES = 227 * 1024;
+constexpr int MEANCLIP_SMEM_MAX_N = 4 * ((SMEM_MAX_BYTES / (TPB * 16)) & ~1);   // 452
+constexpr int MEANCLIP_REG_DEFAULT_MAX_N = 200;  // measured: the register kernel wins wherever it exists (bench.py variants)
 
 struct Bucket { int nb, nlo; };
 // (NLO, NB] buckets.  meanclip goes to 200 frames in registers; sorted to 128.
@@ -541,7 +702,13 @@ Family choose_family(int N, int method, double klo, double khi, int maxiters, in
     if (flags & APGPU_STACK_FORCE_GENERIC) return FAM_GENERIC;
     if (method == APGPU_METHOD_AVERAGE && (maxiters == 0 || (cen == APGPU_CEN_MEAN && dev == APGPU_DEV_STD)) &&
         N >= 3 && klo > 0.0 && khi > 0.0 && klo < 1e6 && khi < 1e6) {
-        if ((*bucket = find_bucket(MEANCLIP_BUCKETS, N))) return FAM_MEANCLIP;
+        const Bucket* rb = find_bucket(MEANCLIP_BUCKETS, N);
+        const bool smem_ok = N <= MEANCLIP_SMEM_MAX_N;
+        bool use_reg = rb && (N <= MEANCLIP_REG_DEFAULT_MAX_N || !smem_ok);
+        if ((flags & APGPU_STACK_PREFER_REGISTERS) && rb) use_reg = true;
+        if ((flags & APGPU_STACK_PREFER_SHARED) && smem_ok) use_reg = false;
+        if (use_reg) { *bucket = rb; return FAM_MEANCLIP; }
+        if (smem_ok) return FAM_MEANCLIP_SMEM;
     }
     if (method == APGPU_METHOD_MEDIAN && maxiters == 0 && !want_uncert) {
         if ((*bucket = find_bucket(SORT_BUCKETS, N))) return FAM_SORT_MED;
@@ -590,6 +757,27 @@ int launch_sorted(const float* const* frames, const StackArgs& a, cudaStream_t s
     return APGPU_OK;
 }
 
+template <int CAP>
+int launch_meanclip_smem(const float* const* frames, const StackArgs& a, cudaStream_t st) {
+    FramePtrs<CAP> fp;
+    for (int i = 0; i < CAP; ++i) fp.p[i] = i < a.N ? frames[i] : nullptr;
+    int64_t blocks = (a.npix + TPB - 1) / TPB;
+    const int n4e = (((a.N + 3) >> 2) + 1) & ~1;
+    size_t smem = (size_t)n4e * TPB * sizeof(float4);
+    const bool sym = (float)a.klo == (float)a.khi;
+    if (sym) {
+        APGPU_CUDA(cudaFuncSetAttribute(stack_meanclip_smem_kernel<true, CAP>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        stack_meanclip_smem_kernel<true, CAP><<<(unsigned)blocks, TPB, smem, st>>>(fp, a);
+    } else {
+        APGPU_CUDA(cudaFuncSetAttribute(stack_meanclip_smem_kernel<false, CAP>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        stack_meanclip_smem_kernel<false, CAP><<<(unsigned)blocks, TPB, smem, st>>>(fp, a);
+    }
+    APGPU_LAUNCH_CHECK("stack_meanclip_smem_kernel");
+    return APGPU_OK;
+}
+
 #define MC_CASE(NB_, NLO_) if (b->nb == NB_) return launch_meanclip<NB_, NLO_>(frames, a, st);
 #define SO_CASE(NB_, NLO_) if (b->nb == NB_) return launch_sorted<NB_, NLO_, MODE>(frames, a, st);
 
@@ -619,6 +807,7 @@ extern "C" const char* apgpu_stack_kernel_name(int N, int method, double k_lo, d
     Family f = choose_family(N, method, k_lo, k_hi, maxiters, cen, dev, want_uncert != 0, flags, &b);
     switch (f) {
         case FAM_MEANCLIP: snprintf(g_kname, sizeof(g_kname), "meanclip<%d>", b->nb); break;
+        case FAM_MEANCLIP_SMEM: snprintf(g_kname, sizeof(g_kname), "meanclip_smem"); break;
         case FAM_SORT_MED: snprintf(g_kname, sizeof(g_kname), "sorted_median<%d>", b->nb); break;
         case FAM_SORT_MEDMAD1: snprintf(g_kname, sizeof(g_kname), "sorted_medmad1<%d>", b->nb); break;
         default: snprintf(g_kname, sizeof(g_kname), "generic<%d>", N <= 32 ? 32 : (N <= 128 ? 128 : 1024)); break;
@@ -638,6 +827,7 @@ extern "C" int apgpu_stack_reduce_f32(const float* const* frames, int N, int64_t
     APGPU_REQUIRE(H > 0 && W > 0 && row0 >= 0 && nrows >= 0 && row0 + nrows <= H,
                   "stack_reduce: bad geometry H=%lld W=%lld row0=%lld nrows=%lld",
                   (long long)H, (long long)W, (long long)row0, (long long)nrows);
+    APGPU_REQUIRE(H * W < ((int64_t)1 << 32), "stack_reduce: frames of %lld pixels exceed the 2^32 limit", (long long)(H * W));
     APGPU_REQUIRE(method >= 0 && method <= 3, "stack_reduce: bad method %d", method);
     APGPU_REQUIRE(cen == APGPU_CEN_MEAN || cen == APGPU_CEN_MEDIAN, "stack_reduce: bad cen %d", cen);
     APGPU_REQUIRE(dev == APGPU_DEV_STD || dev == APGPU_DEV_MAD_STD, "stack_reduce: bad dev %d", dev);
@@ -659,6 +849,8 @@ extern "C" int apgpu_stack_reduce_f32(const float* const* frames, int N, int64_t
     Family f = choose_family(N, method, k_lo, k_hi, maxiters, cen, dev, out_uncert != nullptr, flags, &b);
     switch (f) {
         case FAM_MEANCLIP: return dispatch_meanclip(b, frames, a, st);
+        case FAM_MEANCLIP_SMEM:
+            return N <= 128 ? launch_meanclip_smem<128>(frames, a, st) : launch_meanclip_smem<512>(frames, a, st);
         case FAM_SORT_MED: return dispatch_sorted<MODE_MED>(b, frames, a, st);
         case FAM_SORT_MEDMAD1: return dispatch_sorted<MODE_MEDMAD1>(b, frames, a, st);
         default: break;

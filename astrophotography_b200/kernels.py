@@ -15,6 +15,7 @@ METHODS = {"median": 0, "average": 1, "mean": 1, "min": 2, "max": 3}
 CENFUNCS = {"mean": 0, "median": 1}
 DEVFUNCS = {"std": 0, "mad_std": 1}
 _FORCE_GENERIC = 1
+_PREFER = {None: 0, "registers": 2, "shared": 4}
 
 
 def _stream(torch):
@@ -35,11 +36,12 @@ def _check_image(torch, t, name, dtype=None):
 
 
 def stack_kernel_name(n, method="average", k_lo=5.0, k_hi=5.0, maxiters=1, cen="median",
-                      dev="mad_std", want_uncert=False, out_f64=False, force_generic=False):
+                      dev="mad_std", want_uncert=False, out_f64=False, force_generic=False, prefer=None):
     lib = _native.load()
     return lib.apgpu_stack_kernel_name(
         int(n), METHODS[method], float(k_lo), float(k_hi), _maxiters(maxiters), CENFUNCS[cen],
-        DEVFUNCS[dev], int(want_uncert), int(out_f64), _FORCE_GENERIC if force_generic else 0).decode()
+        DEVFUNCS[dev], int(want_uncert), int(out_f64),
+        (_FORCE_GENERIC if force_generic else 0) | _PREFER[prefer]).decode()
 
 
 def _maxiters(maxiters):
@@ -48,7 +50,7 @@ def _maxiters(maxiters):
 
 def stack_reduce(frames, method="average", k_lo=5.0, k_hi=5.0, maxiters=1, cen="median",
                  dev="mad_std", row0=0, nrows=None, out_f64=False, want_nrej=True,
-                 want_uncert=False, want_allmasked=False, force_generic=False, out=None):
+                 want_uncert=False, want_allmasked=False, force_generic=False, out=None, prefer=None):
     """Per-pixel combine of N frames (``apgpu_stack_reduce_f32``).
 
     ``frames``: a (N,H,W) float32 CUDA tensor or a sequence of N (H,W) float32
@@ -99,7 +101,7 @@ def stack_reduce(frames, method="average", k_lo=5.0, k_hi=5.0, maxiters=1, cen="
         _ptr(nrej), int(nrej is not None and nrej.dtype == torch.uint16),
         _ptr(res.get("uncert") if want_uncert else None),
         _ptr(res.get("allmasked") if want_allmasked else None),
-        _FORCE_GENERIC if force_generic else 0, _stream(torch))
+        (_FORCE_GENERIC if force_generic else 0) | _PREFER[prefer], _stream(torch))
     _native.check(st, "apgpu_stack_reduce_f32")
     return res
 

@@ -272,6 +272,10 @@ def run_gpu(args, shape):
         med = dict(method="median", maxiters=0)
         add_variant("stack_median[%s]" % kernels.stack_kernel_name(n, **med),
                     lambda: kernels.stack_reduce(cube, out=out, want_nrej=False, **med), n * mpix, (4 * n + 4) * h * w)
+        add_variant("stack_kappa_sigma_registers[%s]" % kernels.stack_kernel_name(n, prefer="registers", **HEADLINE),
+                    lambda: kernels.stack_reduce(cube, out=out, prefer="registers", **HEADLINE), n * mpix, alg_bytes)
+        add_variant("stack_kappa_sigma_shared[%s]" % kernels.stack_kernel_name(n, prefer="shared", **HEADLINE),
+                    lambda: kernels.stack_reduce(cube, out=out, prefer="shared", **HEADLINE), n * mpix, alg_bytes)
         c30 = cube[:30]
         add_variant("stack_kappa_sigma_N30[%s]" % kernels.stack_kernel_name(30, **HEADLINE),
                     lambda: kernels.stack_reduce(c30, out=out, **HEADLINE), 30 * mpix, (4 * 30 + 5) * h * w)

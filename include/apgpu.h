@@ -65,13 +65,17 @@ uint64_t apgpu_launch_count(void);
  *             std(kept)/sqrt(n_kept); median: 1.4826*MAD(kept)/sqrt(n_kept)
  * out_allmasked  uint8, 1 where no sample survived (data = NaN there); may be NULL
  * flags       APGPU_STACK_FORCE_GENERIC: use the exact float64 generic kernel
- *             even where a register-resident fast kernel exists
+ *             even where a fast kernel exists; APGPU_STACK_PREFER_REGISTERS /
+ *             APGPU_STACK_PREFER_SHARED: override the default choice between the
+ *             register-resident and shared-memory-resident fast kernels
  * Limits: 1 <= N <= 1024.
  * ---------------------------------------------------------------------- */
 enum { APGPU_METHOD_MEDIAN = 0, APGPU_METHOD_AVERAGE = 1, APGPU_METHOD_MIN = 2, APGPU_METHOD_MAX = 3 };
 enum { APGPU_CEN_MEAN = 0, APGPU_CEN_MEDIAN = 1 };
 enum { APGPU_DEV_STD = 0, APGPU_DEV_MAD_STD = 1 };
 #define APGPU_STACK_FORCE_GENERIC 1
+#define APGPU_STACK_PREFER_REGISTERS 2   /* tuning/tests: register-resident kernel where one exists */
+#define APGPU_STACK_PREFER_SHARED 4      /* tuning/tests: shared-memory-resident kernel where one exists */
 #define APGPU_STACK_MAX_FRAMES 1024
 
 int apgpu_stack_reduce_f32(const float* const* frames, int N, int64_t H, int64_t W,

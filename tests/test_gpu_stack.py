@@ -143,9 +143,14 @@ def test_fast_kernels_match_oracle(cuda, n, case, quantise):
     assert name.startswith(family), name
     st = _stack(n, (9, 70), seed=2, quantise=quantise)
     exp = _oracle(st, method, k_lo, k_hi, maxiters, cen, dev)
-    for out_f64 in (False, True):
+    # the kappa-sigma family has a register-resident and a shared-memory-resident kernel: check both
+    variants = [(f, p) for f in (False, True) for p in (("registers", "shared") if family == "meanclip" else (None,))]
+    for out_f64, prefer in variants:
+        if prefer is not None:
+            kn = kernels.stack_kernel_name(n, method, k_lo, k_hi, maxiters, cen, dev, prefer=prefer)
+            assert kn == ("meanclip_smem" if prefer == "shared" else kn) and kn.startswith("meanclip"), kn
         got = _run(torch, st, method=method, k_lo=k_lo, k_hi=k_hi, maxiters=maxiters, cen=cen, dev=dev,
-                   out_f64=out_f64)
+                   out_f64=out_f64, prefer=prefer)
         assert np.array_equal(got["nrej"].astype(np.int64), exp["nrej"]), (name, out_f64)
         assert np.array_equal(got["allmasked"], exp["allmasked"])
         if family == "sorted_median":
@@ -159,14 +164,16 @@ def test_fast_kernels_match_oracle(cuda, n, case, quantise):
             _assert_close_data(got["data"].astype(np.float64), exp["data"], rt, 12.0)
 
 
-@pytest.mark.parametrize("n", [130, 160, 200])
-def test_meanclip_large_n(cuda, n):
+@pytest.mark.parametrize("n", [130, 160, 200, 257, 448])
+@pytest.mark.parametrize("prefer", ["registers", "shared"])
+def test_meanclip_large_n(cuda, n, prefer):
     torch = cuda
     from astrophotography_b200 import kernels
     assert kernels.stack_kernel_name(n, "average", 3, 3, 5, "mean", "std").startswith("meanclip")
     st = _stack(n, (6, 64), seed=4)
     exp = _oracle(st, "average", 3.0, 3.0, 5, "mean", "std")
-    got = _run(torch, st, method="average", k_lo=3.0, k_hi=3.0, maxiters=5, cen="mean", dev="std", want_uncert=True)
+    got = _run(torch, st, method="average", k_lo=3.0, k_hi=3.0, maxiters=5, cen="mean", dev="std", want_uncert=True,
+               prefer=prefer)
     assert np.array_equal(got["nrej"].astype(np.int64), exp["nrej"])
     _assert_close_data(got["data"].astype(np.float64), exp["data"], RTOL32, 1.0)
     _assert_close_data(got["uncert"].astype(np.float64), exp["uncert"], 1e-5, 1e-3)
