@@ -42,7 +42,6 @@ SIGNATURES = {
     "apgpu_sigma_clipped_stats_f32": (_c.c_int, [_P, _c.c_int64, _c.c_double, _c.c_int, _P,
                                                  _c.c_size_t, _P, _P]),
     "apgpu_threshold_mask_f32": (_c.c_int, [_P, _c.c_int64, _c.c_double, _c.c_double, _P, _P, _P]),
-    "apgpu_imarith_f32": (_c.c_int, [_P, _P, _c.c_float, _c.c_int, _P, _c.c_int64, _P]),
 }
 
 _lib = None

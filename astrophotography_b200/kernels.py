@@ -213,3 +213,34 @@ def fix_badpix(data, mask, deltapix=1, min_valid=4, image_rows=None, band_row0=0
                                   _ptr(out), _ptr(counts), _stream(torch))
     _native.check(st, "apgpu_fix_badpix_f32")
     return out, counts
+
+
+def sigma_clipped_stats(data, sigma=3.0, maxiters=5):
+    """``astropy.stats.sigma_clipped_stats(data, sigma=sigma)`` over a float32 CUDA image.
+
+    Returns ``(mean, median, std, count)`` of the surviving pixels as Python
+    numbers (one small device-to-host read)."""
+    torch = _native.require_cuda()
+    lib = _native.load()
+    _check_image(torch, data, "data", torch.float32)
+    npix = data.numel()
+    nbytes = int(lib.apgpu_image_stats_workspace_bytes(npix))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=data.device)
+    out4 = torch.empty(4, dtype=torch.float64, device=data.device)
+    _native.check(lib.apgpu_sigma_clipped_stats_f32(_ptr(data), npix, float(sigma), int(maxiters), _ptr(ws),
+                                                    nbytes, _ptr(out4), _stream(torch)),
+                  "apgpu_sigma_clipped_stats_f32")
+    mean, med, std, cnt = out4.cpu().tolist()
+    return mean, med, std, int(cnt)
+
+
+def threshold_mask(data, lo, hi):
+    """uint8 mask ``(data < lo) | (data > hi)`` and the number of set pixels."""
+    torch = _native.require_cuda()
+    lib = _native.load()
+    _check_image(torch, data, "data", torch.float32)
+    mask = torch.empty(data.shape, dtype=torch.uint8, device=data.device)
+    nbad = torch.zeros(1, dtype=torch.int64, device=data.device)
+    _native.check(lib.apgpu_threshold_mask_f32(_ptr(data), data.numel(), float(lo), float(hi), _ptr(mask),
+                                               _ptr(nbad), _stream(torch)), "apgpu_threshold_mask_f32")
+    return mask, int(nbad.item())

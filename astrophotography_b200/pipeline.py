@@ -137,3 +137,57 @@ class HostStackCombiner:
                 reduced[buf] = ev
         self.compute_stream.synchronize()
         return {k: arr for k, (arr, _) in self.host_out.items()}
+
+
+def combine_sharded(frames, reduce_band=None, dist=None, **combine_kw):
+    """Row-band sharded combine across the ranks of ``torch.distributed`` (one process per GPU).
+
+    Every rank holds (or can read) the same N host frames, reduces only its own
+    row band (``row_band``) and the bands are gathered on rank 0; there is no
+    data-path collective because each output pixel depends only on the same
+    pixel of the N frames.  ``reduce_band(list_of_band_arrays)
+    -> dict`` defaults to the GPU ``HostStackCombiner``; tests inject the CPU
+    oracle to exercise this host logic under the ``gloo`` backend.
+
+    Returns the dict of full-frame host arrays on rank 0 and ``None`` elsewhere.
+    """
+    import torch
+    if dist is None:
+        import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    n = len(frames)
+    h, w = frames[0].shape
+    r0, r1, _, _ = row_band(h, world, rank)
+    bands = [np.ascontiguousarray(f[r0:r1]) for f in frames]
+    if reduce_band is None:
+        def reduce_band(bs):
+            comb = HostStackCombiner(n, r1 - r0, w, **combine_kw)
+            return {k: np.array(v, copy=True) for k, v in comb.combine(bs).items()}
+    local = reduce_band(bands) if r1 > r0 else {}
+    if world == 1:
+        return local
+    max_rows = (h + world - 1) // world
+    keys = sorted(local.keys()) if r1 > r0 else None
+    key_lists = [None] * world
+    dist.all_gather_object(key_lists, (keys, {k: str(local[k].dtype) for k in (keys or [])}))
+    keys, dtypes = next(kl for kl in key_lists if kl[0] is not None)
+    backend = dist.get_backend()
+    device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    out = {} if rank == 0 else None
+    for k in keys:
+        dt = np.dtype(dtypes[k])
+        pad = np.zeros((max_rows, w), dtype=dt)
+        if r1 > r0:
+            pad[: r1 - r0] = local[k]
+        t = torch.from_numpy(pad.view(np.uint8).reshape(max_rows, w * dt.itemsize)).to(device)   # raw bytes: any dtype, any backend
+        recv = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
+        dist.gather(t, recv, dst=0)
+        if rank == 0:
+            full = np.empty((h, w), dtype=dt)
+            for rk in range(world):
+                a0, a1, _, _ = row_band(h, world, rk)
+                part = recv[rk].cpu().numpy().view(dt).reshape(max_rows, w)
+                full[a0:a1] = part[: a1 - a0]
+            out[k] = full
+    return out

@@ -150,6 +150,26 @@ int apgpu_fix_badpix_f32(const float* data, const void* mask, int mask_dtype,
                          int64_t row0, int64_t nrows, int deltapix, int min_valid,
                          float* out, int64_t* counts, apgpu_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * Whole-image sigma-clipped statistics and threshold mask: the arithmetic of the
+ * mask producer ApFindBadPixels._generate_sigmaclip_mask,
+ * core/ApFindBadPixels.py:191-209.
+ *
+ * apgpu_sigma_clipped_stats_f32 restates astropy.stats.sigma_clipped_stats(data,
+ * sigma) with its defaults (median centre, population std, maxiters clip rounds)
+ * over the finite pixels and writes {mean, median, std, count} of the survivors
+ * to out4 (device, 4 doubles).  The median is exact (radix select).
+ * apgpu_threshold_mask_f32 writes mask = (data < lo) | (data > hi) as uint8
+ * (comparison in float64, as numpy promotes) and adds the number of set pixels
+ * to *nbad (device int64, caller zeroes it).
+ * ---------------------------------------------------------------------- */
+size_t apgpu_image_stats_workspace_bytes(int64_t npix);
+int apgpu_sigma_clipped_stats_f32(const float* data, int64_t npix, double sigma, int maxiters,
+                                  void* workspace, size_t workspace_bytes, double* out4,
+                                  apgpu_stream_t stream);
+int apgpu_threshold_mask_f32(const float* data, int64_t npix, double lo, double hi,
+                             uint8_t* mask, int64_t* nbad, apgpu_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
