@@ -41,7 +41,11 @@ class ApFixBadPixels(ApBase):
         # the reference's ApFixBadPixels._read_fits (:92-153) keeps the file's dtype
         idata, ihdr, ped = self._read_fits(inpdata_file, ext_num, to_float=False)
         if ped != 0:
-            idata = idata + idata.dtype.type(ped) if np.issubdtype(idata.dtype, np.floating) else idata + int(ped)
+            # (the reference's in-place ``ext_data += pedestal`` raises for integer images, :147;
+            #  here an integer image with a PEDESTAL is promoted to float32 first)
+            if not np.issubdtype(idata.dtype, np.floating):
+                idata = idata.astype(np.float32)
+            idata = idata + idata.dtype.type(ped)
         mskdata, _, _ = self._read_fits(badpixmask_file, ext_num, to_float=False)
         odata, odict = self.fix_bad_pixels(idata, mskdata, deltapix)
         odict["BPIXFILE"] = (Path(badpixmask_file).name, "Name of master bad pixel file used")
