@@ -238,24 +238,20 @@ __device__ __forceinline__ float med3(float a, float b, float c) {
 // (t = y - c), 4 FADD2 + 4 FFMA2 (sums), the |t| maximum, one compare -- no
 // per-sample predicates or selects.  Only a group whose largest |y - c| reaches
 // the inner clip bound is revisited, sample by sample, in a second "rare" pass.
+constexpr int meanclip_min_blocks(int NB) {
+    return NB <= 32 ? 6 : (NB <= 48 ? 5 : (NB <= 100 ? 4 : (NB <= 128 ? 3 : 2)));
+}
+
+// The per-pixel work, given the N raw samples of pixel p in y[] (padding = 0).
 template <int NB, int NLO, bool SYM>
-__global__ void __launch_bounds__(TPB, (NB <= 32 ? 6 : (NB <= 48 ? 5 : (NB <= 100 ? 4 : (NB <= 128 ? 3 : 2)))))
-stack_meanclip_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_constant__ StackArgs a) {
+__device__ __forceinline__ void meanclip_pixel(float2 (&y)[NB / 2], const FramePtrs<NB>& fp,
+                                               const StackArgs& a, const int64_t p) {
     static_assert(NB % 2 == 0, "meanclip buckets must be even");
-    const int64_t p = a.pix0 + (int64_t)blockIdx.x * TPB + threadIdx.x;
-    if (p >= a.pix0 + a.npix) return;
     const int N = a.N;
     constexpr int NP = NB / 2;                         // register pairs
     constexpr int GP = 4;                              // pairs (8 samples) per group
     constexpr int NG = (NP + GP - 1) / GP;
     static_assert(NG <= 64, "flag word too small");
-    const uint32_t p32 = (uint32_t)p;                  // host guarantees H*W < 2^32
-    float2 y[NP];
-#pragma unroll
-    for (int j = 0; j < NP; ++j) {
-        y[j].x = APGPU_ACTIVE(2 * j) ? ld_stream(fp.p[2 * j] + p32) : 0.f;
-        y[j].y = APGPU_ACTIVE(2 * j + 1) ? ld_stream(fp.p[2 * j + 1] + p32) : 0.f;
-    }
 
     // Pivot: median of the first three frames (robust to one outlier).  All
     // float32 arithmetic below is on y = x - pivot: sums stay small and the
@@ -404,6 +400,107 @@ stack_meanclip_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_con
         unc_out = __ddiv_rn(__dsqrt_rn(var > 0.0 ? var : 0.0), __dsqrt_rn((double)nk));
     }
     write_pixel(a, p, mean, N - nk, unc_out, 0);
+}
+
+// Direct kernel: one block per 128-pixel tile, samples loaded straight from
+// global memory.
+template <int NB, int NLO, bool SYM>
+__global__ void __launch_bounds__(TPB, meanclip_min_blocks(NB))
+stack_meanclip_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_constant__ StackArgs a) {
+    const int64_t p = a.pix0 + (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (p >= a.pix0 + a.npix) return;
+    const int N = a.N;
+    const uint32_t p32 = (uint32_t)p;                  // host guarantees H*W < 2^32
+    float2 y[NB / 2];
+#pragma unroll
+    for (int j = 0; j < NB / 2; ++j) {
+        y[j].x = APGPU_ACTIVE(2 * j) ? ld_stream(fp.p[2 * j] + p32) : 0.f;
+        y[j].y = APGPU_ACTIVE(2 * j + 1) ? ld_stream(fp.p[2 * j + 1] + p32) : 0.f;
+    }
+    meanclip_pixel<NB, NLO, SYM>(y, fp, a, p);
+}
+
+// ---------------------------------------------------------------------------
+// TMA-staged persistent kernel (opt-in: APGPU_STACK_USE_TMA)
+// ---------------------------------------------------------------------------
+// meanclip_min_blocks(NB)/2 persistent 256-thread CTAs per SM walk the 256-pixel
+// tiles of the band.  For each tile one warp issues N bulk asynchronous copies
+// (cp.async.bulk global -> shared, 1 KB contiguous of each frame, completion
+// counted on an mbarrier); the threads pull their column out of shared memory
+// into registers (conflict-free LDS), release the stage with one __syncthreads,
+// and the copies for the CTA's NEXT tile are issued before the arithmetic on the
+// current one starts.  Measured on B200 (profiles/): correct, but 20 % SLOWER
+// than the direct kernel at N=100 -- the per-tile CTA barrier makes every warp
+// wait for the CTA's slowest pixel (clip iteration counts differ per pixel) --
+// so the dispatcher only uses it on request.
+__device__ __forceinline__ uint32_t smem_u32(const void* ptr) {
+    return (uint32_t)__cvta_generic_to_shared(ptr);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "APGPU_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra APGPU_DONE;\n"
+        "bra APGPU_WAIT;\n"
+        "APGPU_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// Threads (= pixels) per CTA of the TMA-staged kernel: 256, so that every bulk copy
+// moves 1 KB (512-byte copies are TMA-issue bound).
+constexpr int TTPB = 256;
+
+template <int NB>
+__device__ __forceinline__ void issue_tile_copies(const FramePtrs<NB>& fp, int N, int64_t pix, float* stage,
+                                                  uint64_t* bar) {
+    // called by warp 0
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) mbar_expect_tx(bar, (uint32_t)N * TTPB * sizeof(float));
+    __syncwarp();
+    for (int i = lane; i < N; i += 32)
+        bulk_copy_g2s(stage + i * TTPB, fp.p[i] + pix, TTPB * sizeof(float), bar);
+}
+
+template <int NB, int NLO, bool SYM>
+__global__ void __launch_bounds__(TTPB, meanclip_min_blocks(NB) / 2)
+stack_meanclip_tma_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_constant__ StackArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* stage = reinterpret_cast<float*>(smem_raw);                       // [NB][TTPB]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NB * TTPB * sizeof(float));
+    const int N = a.N;
+    const int64_t ntiles = a.npix / TTPB;                                    // full tiles only (host launches the tail)
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    __syncthreads();
+    int64_t tile = blockIdx.x;
+    uint32_t parity = 0;
+    if (tile < ntiles && threadIdx.x < 32) issue_tile_copies<NB>(fp, N, a.pix0 + tile * TTPB, stage, bar);
+    for (; tile < ntiles; tile += gridDim.x) {
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+        float2 y[NB / 2];
+#pragma unroll
+        for (int j = 0; j < NB / 2; ++j) {
+            y[j].x = APGPU_ACTIVE(2 * j) ? stage[(2 * j) * TTPB + threadIdx.x] : 0.f;
+            y[j].y = APGPU_ACTIVE(2 * j + 1) ? stage[(2 * j + 1) * TTPB + threadIdx.x] : 0.f;
+        }
+        __syncthreads();                                                     // every thread has drained the stage
+        const int64_t next = tile + gridDim.x;
+        if (next < ntiles && threadIdx.x < 32) issue_tile_copies<NB>(fp, N, a.pix0 + next * TTPB, stage, bar);
+        meanclip_pixel<NB, NLO, SYM>(y, fp, a, a.pix0 + tile * TTPB + threadIdx.x);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -730,17 +827,42 @@ int launch_generic(const float* const* frames, const StackArgs& a, cudaStream_t 
     return APGPU_OK;
 }
 
+template <int NB, int NLO, bool SYM>
+int launch_meanclip_sym(const FramePtrs<NB>& fp, const StackArgs& a, bool use_tma, cudaStream_t st) {
+    StackArgs rest = a;
+    if constexpr (meanclip_min_blocks(NB) % 2 == 0) {
+        if (use_tma) {
+            const int64_t ntiles = a.npix / TTPB;
+            if (ntiles > 0) {
+                const size_t smem = (size_t)NB * TTPB * sizeof(float) + 16;
+                APGPU_CUDA(cudaFuncSetAttribute(stack_meanclip_tma_kernel<NB, NLO, SYM>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                int64_t grid = (int64_t)APGPU_NUM_SMS * (meanclip_min_blocks(NB) / 2);
+                if (grid > ntiles) grid = ntiles;
+                stack_meanclip_tma_kernel<NB, NLO, SYM><<<(unsigned)grid, TTPB, smem, st>>>(fp, a);
+                APGPU_LAUNCH_CHECK("stack_meanclip_tma_kernel");
+            }
+            rest.pix0 = a.pix0 + ntiles * TTPB;      // the < 256-pixel tail goes through the direct kernel
+            rest.npix = a.npix - ntiles * TTPB;
+        }
+    }
+    if (rest.npix > 0) {
+        int64_t blocks = (rest.npix + TPB - 1) / TPB;
+        stack_meanclip_kernel<NB, NLO, SYM><<<(unsigned)blocks, TPB, 0, st>>>(fp, rest);
+        APGPU_LAUNCH_CHECK("stack_meanclip_kernel");
+    }
+    return APGPU_OK;
+}
+
 template <int NB, int NLO>
-int launch_meanclip(const float* const* frames, const StackArgs& a, cudaStream_t st) {
+int launch_meanclip(const float* const* frames, const StackArgs& a, cudaStream_t st, int flags) {
     FramePtrs<NB> fp;
     for (int i = 0; i < NB; ++i) fp.p[i] = i < a.N ? frames[i] : nullptr;
-    int64_t blocks = (a.npix + TPB - 1) / TPB;
-    if ((float)a.klo == (float)a.khi)
-        stack_meanclip_kernel<NB, NLO, true><<<(unsigned)blocks, TPB, 0, st>>>(fp, a);
-    else
-        stack_meanclip_kernel<NB, NLO, false><<<(unsigned)blocks, TPB, 0, st>>>(fp, a);
-    APGPU_LAUNCH_CHECK("stack_meanclip_kernel");
-    return APGPU_OK;
+    // bulk copies need 16-byte aligned sources: frame base + first pixel of the band
+    bool use_tma = (flags & APGPU_STACK_USE_TMA) != 0;
+    for (int i = 0; i < a.N; ++i) use_tma = use_tma && apgpu_aligned(frames[i] + a.pix0, 16);
+    if ((float)a.klo == (float)a.khi) return launch_meanclip_sym<NB, NLO, true>(fp, a, use_tma, st);
+    return launch_meanclip_sym<NB, NLO, false>(fp, a, use_tma, st);
 }
 
 template <int NB, int NLO, int MODE>
@@ -778,10 +900,10 @@ int launch_meanclip_smem(const float* const* frames, const StackArgs& a, cudaStr
     return APGPU_OK;
 }
 
-#define MC_CASE(NB_, NLO_) if (b->nb == NB_) return launch_meanclip<NB_, NLO_>(frames, a, st);
+#define MC_CASE(NB_, NLO_) if (b->nb == NB_) return launch_meanclip<NB_, NLO_>(frames, a, st, flags);
 #define SO_CASE(NB_, NLO_) if (b->nb == NB_) return launch_sorted<NB_, NLO_, MODE>(frames, a, st);
 
-int dispatch_meanclip(const Bucket* b, const float* const* frames, const StackArgs& a, cudaStream_t st) {
+int dispatch_meanclip(const Bucket* b, const float* const* frames, const StackArgs& a, cudaStream_t st, int flags) {
     MC_CASE(8, 2) MC_CASE(16, 8) MC_CASE(24, 16) MC_CASE(32, 24) MC_CASE(48, 32) MC_CASE(64, 48)
     MC_CASE(80, 64) MC_CASE(100, 80) MC_CASE(128, 100) MC_CASE(160, 128) MC_CASE(200, 160)
     return APGPU_ERR_UNSUPPORTED;
@@ -848,7 +970,7 @@ extern "C" int apgpu_stack_reduce_f32(const float* const* frames, int N, int64_t
     const Bucket* b = nullptr;
     Family f = choose_family(N, method, k_lo, k_hi, maxiters, cen, dev, out_uncert != nullptr, flags, &b);
     switch (f) {
-        case FAM_MEANCLIP: return dispatch_meanclip(b, frames, a, st);
+        case FAM_MEANCLIP: return dispatch_meanclip(b, frames, a, st, flags);
         case FAM_MEANCLIP_SMEM:
             return N <= 128 ? launch_meanclip_smem<128>(frames, a, st) : launch_meanclip_smem<512>(frames, a, st);
         case FAM_SORT_MED: return dispatch_sorted<MODE_MED>(b, frames, a, st);

@@ -144,11 +144,13 @@ def test_fast_kernels_match_oracle(cuda, n, case, quantise):
     st = _stack(n, (9, 70), seed=2, quantise=quantise)
     exp = _oracle(st, method, k_lo, k_hi, maxiters, cen, dev)
     # the kappa-sigma family has a register-resident and a shared-memory-resident kernel: check both
-    variants = [(f, p) for f in (False, True) for p in (("registers", "shared") if family == "meanclip" else (None,))]
+    variants = [(f, p) for f in (False, True)
+                for p in (("registers", "registers_tma", "shared") if family == "meanclip" else (None,))]
     for out_f64, prefer in variants:
         if prefer is not None:
             kn = kernels.stack_kernel_name(n, method, k_lo, k_hi, maxiters, cen, dev, prefer=prefer)
             assert kn == ("meanclip_smem" if prefer == "shared" else kn) and kn.startswith("meanclip"), kn
+        # (9, 70) = 630 pixels: 4 full TMA tiles + a 118-pixel tail through the direct kernel
         got = _run(torch, st, method=method, k_lo=k_lo, k_hi=k_hi, maxiters=maxiters, cen=cen, dev=dev,
                    out_f64=out_f64, prefer=prefer)
         assert np.array_equal(got["nrej"].astype(np.int64), exp["nrej"]), (name, out_f64)
