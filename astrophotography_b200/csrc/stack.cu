@@ -38,6 +38,7 @@ namespace {
 
 constexpr double MAD_TO_STD = 1.482602218505602;   // astropy.stats.mad_std scale
 constexpr int TPB = 128;                           // threads (= pixels) per block
+constexpr int SMEM_MAX_BYTES = 227 * 1024;         // opt-in dynamic shared memory per CTA / per SM budget
 
 struct StackArgs {
     int N, method, maxiters, cen, dev;
@@ -504,6 +505,66 @@ stack_meanclip_tma_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid
 }
 
 // ---------------------------------------------------------------------------
+// cp.async-staged persistent kernel: warp-granular software pipeline
+// ---------------------------------------------------------------------------
+// Every warp is its own pipeline: it owns a private [N][32-pixel] shared-memory
+// stage, fills it with 16-byte asynchronous copies (cp.async / LDGSTS: one warp
+// instruction moves the 128-byte rows of four frames), drains it into registers,
+// immediately re-arms it with the copies for its NEXT tile and only then does
+// the arithmetic.  No CTA barrier anywhere, so a warp never waits for another
+// warp's slow pixel (the flaw of the CTA-wide TMA variant above), the HBM latency
+// of tile t+1 hides behind the compute of tile t without extra registers, and
+// the instruction stream has 1/4 of the load instructions and no per-sample
+// 64-bit address arithmetic.
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+constexpr int WT = 32;      // pixels per warp tile
+
+__device__ __forceinline__ void issue_warp_tile(const float* const* ptab, int N, int64_t pix, float* stage, int lane) {
+    const int sub = lane >> 3;            // which of the 4 frames of this instruction
+    const int off = (lane & 7) * 4;       // 4 pixels (16 bytes) per lane
+    for (int i0 = 0; i0 < N; i0 += 4) {
+        const int i = i0 + sub;
+        if (i < N) cp_async16(stage + i * WT + off, ptab[i] + pix + off);
+    }
+    cp_async_commit();
+}
+
+template <int NB, int NLO, bool SYM>
+__global__ void __launch_bounds__(TPB, meanclip_min_blocks(NB))
+stack_meanclip_cpasync_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_constant__ StackArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const float** ptab = reinterpret_cast<const float**>(smem_raw);           // [NB] frame pointers
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* stage = reinterpret_cast<float*>(smem_raw + (size_t)NB * sizeof(float*)) + (size_t)warp * NB * WT;
+    const int N = a.N;
+    for (int i = threadIdx.x; i < N; i += TPB) ptab[i] = fp.p[i];
+    __syncthreads();
+    const int64_t ntiles = a.npix / WT;                                       // full warp tiles (host launches the tail)
+    const int64_t nwarps = (int64_t)gridDim.x * (TPB / 32);
+    int64_t tile = (int64_t)blockIdx.x * (TPB / 32) + warp;
+    if (tile < ntiles) issue_warp_tile(ptab, N, a.pix0 + tile * WT, stage, lane);
+    for (; tile < ntiles; tile += nwarps) {
+        cp_async_wait_all();
+        __syncwarp();                                                         // every lane's copies are visible
+        float2 y[NB / 2];
+#pragma unroll
+        for (int j = 0; j < NB / 2; ++j) {
+            y[j].x = APGPU_ACTIVE(2 * j) ? stage[(2 * j) * WT + lane] : 0.f;
+            y[j].y = APGPU_ACTIVE(2 * j + 1) ? stage[(2 * j + 1) * WT + lane] : 0.f;
+        }
+        __syncwarp();                                                         // stage drained by every lane
+        const int64_t next = tile + nwarps;
+        if (next < ntiles) issue_warp_tile(ptab, N, a.pix0 + next * WT, stage, lane);
+        meanclip_pixel<NB, NLO, SYM>(y, fp, a, a.pix0 + tile * WT + lane);
+    }
+}
+
+// ---------------------------------------------------------------------------
 // meanclip_smem<SYM, CAP>: the same algorithm with the pixel's samples parked in
 // shared memory instead of registers, any N that fits (N <= ~450).
 // ---------------------------------------------------------------------------
@@ -775,7 +836,6 @@ stack_sorted_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_const
 // ---------------------------------------------------------------------------
 enum Family { FAM_GENERIC = 0, FAM_MEANCLIP = 1, FAM_SORT_MED = 2, FAM_SORT_MEDMAD1 = 3, FAM_MEANCLIP_SMEM = 4 };
 
-constexpr int SMEM_MAX_BYTES = 227 * 1024;
 constexpr int MEANCLIP_SMEM_MAX_N = 4 * ((SMEM_MAX_BYTES / (TPB * 16)) & ~1);   // 452
 constexpr int MEANCLIP_REG_DEFAULT_MAX_N = 200;  // measured: the register kernel wins wherever it exists (bench.py variants)
 
@@ -828,10 +888,26 @@ int launch_generic(const float* const* frames, const StackArgs& a, cudaStream_t 
 }
 
 template <int NB, int NLO, bool SYM>
-int launch_meanclip_sym(const FramePtrs<NB>& fp, const StackArgs& a, bool use_tma, cudaStream_t st) {
+int launch_meanclip_sym(const FramePtrs<NB>& fp, const StackArgs& a, int staging, cudaStream_t st) {
+    // staging: 0 direct global loads, 1 CTA-wide TMA bulk copies, 2 warp-granular cp.async pipeline
     StackArgs rest = a;
+    if (staging == 2) {
+        const int64_t ntiles = a.npix / WT;
+        if (ntiles > 0) {
+            const size_t smem = (size_t)NB * sizeof(float*) + (size_t)(TPB / 32) * NB * WT * sizeof(float);
+            APGPU_CUDA(cudaFuncSetAttribute(stack_meanclip_cpasync_kernel<NB, NLO, SYM>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int64_t grid = (int64_t)APGPU_NUM_SMS * meanclip_min_blocks(NB);
+            const int64_t need = (ntiles + TPB / 32 - 1) / (TPB / 32);
+            if (grid > need) grid = need;
+            stack_meanclip_cpasync_kernel<NB, NLO, SYM><<<(unsigned)grid, TPB, smem, st>>>(fp, a);
+            APGPU_LAUNCH_CHECK("stack_meanclip_cpasync_kernel");
+        }
+        rest.pix0 = a.pix0 + ntiles * WT;            // the < 32-pixel tail goes through the direct kernel
+        rest.npix = a.npix - ntiles * WT;
+    }
     if constexpr (meanclip_min_blocks(NB) % 2 == 0) {
-        if (use_tma) {
+        if (staging == 1) {
             const int64_t ntiles = a.npix / TTPB;
             if (ntiles > 0) {
                 const size_t smem = (size_t)NB * TTPB * sizeof(float) + 16;
@@ -858,11 +934,18 @@ template <int NB, int NLO>
 int launch_meanclip(const float* const* frames, const StackArgs& a, cudaStream_t st, int flags) {
     FramePtrs<NB> fp;
     for (int i = 0; i < NB; ++i) fp.p[i] = i < a.N ? frames[i] : nullptr;
-    // bulk copies need 16-byte aligned sources: frame base + first pixel of the band
-    bool use_tma = (flags & APGPU_STACK_USE_TMA) != 0;
-    for (int i = 0; i < a.N; ++i) use_tma = use_tma && apgpu_aligned(frames[i] + a.pix0, 16);
-    if ((float)a.klo == (float)a.khi) return launch_meanclip_sym<NB, NLO, true>(fp, a, use_tma, st);
-    return launch_meanclip_sym<NB, NLO, false>(fp, a, use_tma, st);
+    // asynchronous copies need 16-byte aligned sources: frame base + first pixel of the band
+    // default (measured, bench.py variants): the warp-granular cp.async pipeline wins for the
+    // shorter stacks (N=30: +8 %), direct loads are level or slightly ahead from N~80 up
+    int staging = (flags & APGPU_STACK_USE_TMA) ? 1 : ((flags & APGPU_STACK_DIRECT_LOADS) ? 0 : (NB <= 64 ? 2 : 0));
+    if (flags & APGPU_STACK_USE_CPASYNC) staging = 2;
+    // the per-warp stages must leave room for meanclip_min_blocks CTAs per SM
+    const size_t smem_cta = (size_t)NB * sizeof(float*) + (size_t)(TPB / 32) * NB * WT * sizeof(float);
+    if (staging == 2 && smem_cta * meanclip_min_blocks(NB) > (size_t)SMEM_MAX_BYTES) staging = 0;
+    for (int i = 0; i < a.N; ++i)
+        if (!apgpu_aligned(frames[i] + a.pix0, 16)) staging = 0;
+    if ((float)a.klo == (float)a.khi) return launch_meanclip_sym<NB, NLO, true>(fp, a, staging, st);
+    return launch_meanclip_sym<NB, NLO, false>(fp, a, staging, st);
 }
 
 template <int NB, int NLO, int MODE>

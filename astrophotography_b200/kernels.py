@@ -15,7 +15,8 @@ METHODS = {"median": 0, "average": 1, "mean": 1, "min": 2, "max": 3}
 CENFUNCS = {"mean": 0, "median": 1}
 DEVFUNCS = {"std": 0, "mad_std": 1}
 _FORCE_GENERIC = 1
-_PREFER = {None: 0, "registers": 2, "shared": 4, "registers_tma": 2 | 8, "tma": 8}
+_PREFER = {None: 0, "registers": 2, "shared": 4, "registers_tma": 2 | 8, "tma": 8,
+           "registers_direct": 2 | 16, "direct": 16, "registers_cpasync": 2 | 32, "cpasync": 32}
 
 
 def _stream(torch):

@@ -76,7 +76,9 @@ enum { APGPU_DEV_STD = 0, APGPU_DEV_MAD_STD = 1 };
 #define APGPU_STACK_FORCE_GENERIC 1
 #define APGPU_STACK_PREFER_REGISTERS 2   /* tuning/tests: register-resident kernel where one exists */
 #define APGPU_STACK_PREFER_SHARED 4      /* tuning/tests: shared-memory-resident kernel where one exists */
-#define APGPU_STACK_USE_TMA 8            /* tuning/tests: TMA-staged persistent kernel (slower than direct loads) */
+#define APGPU_STACK_USE_TMA 8            /* tuning/tests: CTA-wide TMA bulk-copy staging */
+#define APGPU_STACK_DIRECT_LOADS 16      /* tuning/tests: direct global loads, no shared-memory staging */
+#define APGPU_STACK_USE_CPASYNC 32       /* tuning/tests: warp-granular cp.async staging pipeline */
 #define APGPU_STACK_MAX_FRAMES 1024
 
 int apgpu_stack_reduce_f32(const float* const* frames, int N, int64_t H, int64_t W,

@@ -145,7 +145,7 @@ def test_fast_kernels_match_oracle(cuda, n, case, quantise):
     exp = _oracle(st, method, k_lo, k_hi, maxiters, cen, dev)
     # the kappa-sigma family has a register-resident and a shared-memory-resident kernel: check both
     variants = [(f, p) for f in (False, True)
-                for p in (("registers", "registers_tma", "shared") if family == "meanclip" else (None,))]
+                for p in (("registers", "registers_tma", "registers_direct", "registers_cpasync", "shared") if family == "meanclip" else (None,))]
     for out_f64, prefer in variants:
         if prefer is not None:
             kn = kernels.stack_kernel_name(n, method, k_lo, k_hi, maxiters, cen, dev, prefer=prefer)
