@@ -6,10 +6,11 @@
 // the image (:383-394), provided at least min_valid=4 good ones exist (:397).
 //
 // Here: one dense pass, HBM-bound (4 B read + mask + 4 B write per pixel).  Each
-// thread copies four adjacent pixels with 128-bit accesses; a lane that meets a
-// bad pixel gathers the <= 24 donors of the 5x5 window (neighbour rows are L1/L2
-// hits: the warp has just streamed them) into registers, sorts them with a
-// Batcher network (+inf padding for non-donors) and picks the middle order
+// thread copies four adjacent pixels with 128-bit accesses.  When a warp meets
+// bad pixels it repairs them one after the other COOPERATIVELY: the 32 lanes
+// fetch the <= 24 donors of the 5x5 window in parallel (neighbour rows are L1/L2
+// hits: the warp has just streamed them), sort them with a bitonic network of
+// warp shuffles (+inf for non-donors) and read back the middle order
 // statistics.  Donors come from the input image only, so every pixel is
 // independent: no halo exchange, no second pass.
 //
@@ -19,64 +20,11 @@
 #include <math.h>
 
 #include "apgpu_common.cuh"
-#include "sort_networks.inc"
 
 namespace {
 
 template <typename MaskT>
 __device__ __forceinline__ bool mask_bad(const MaskT* m, int64_t i) { return m[i] != (MaskT)0; }
-
-#define CE_V(i, j) { float lo_ = fminf(v[i], v[j]); float hi_ = fmaxf(v[i], v[j]); v[i] = lo_; v[j] = hi_; }
-
-template <int NV> __device__ __forceinline__ void sort_donors(float (&v)[NV]);
-template <> __device__ __forceinline__ void sort_donors<8>(float (&v)[8]) { APGPU_SORTNET_8(CE_V) }
-template <> __device__ __forceinline__ void sort_donors<24>(float (&v)[24]) { APGPU_SORTNET_24(CE_V) }
-
-template <int NV>
-__device__ __forceinline__ float pick(const float (&v)[NV], int k) {
-    float r = v[0];
-#pragma unroll
-    for (int i = 1; i < NV; ++i) r = (i == k) ? v[i] : r;
-    return r;
-}
-
-// Median of the good neighbours of bad pixel (r, c); returns false when fewer
-// than min_valid good neighbours exist.  DP in {1, 2}: register network.
-template <int DP, typename MaskT>
-__device__ __noinline__ bool repair_small(const float* __restrict__ data, const MaskT* __restrict__ mask,
-                                          int64_t H, int64_t W, int64_t band_row0,
-                                          int64_t r, int64_t c, int min_valid, float& result) {
-    constexpr int NV = (2 * DP + 1) * (2 * DP + 1) - 1;
-    float v[NV];
-    int ngood = 0;
-    bool anynan = false;
-    int k = 0;
-#pragma unroll
-    for (int dr = -DP; dr <= DP; ++dr) {
-#pragma unroll
-        for (int dc = -DP; dc <= DP; ++dc) {
-            if (dr == 0 && dc == 0) continue;       // the centre is bad: never a donor
-            int64_t rr = r + dr, cc = c + dc;
-            float val = INFINITY;
-            if (rr >= 0 && rr < H && cc >= 0 && cc < W) {
-                int64_t idx = (rr - band_row0) * W + cc;
-                if (!mask_bad(mask, idx)) {
-                    float x = data[idx];
-                    ++ngood;
-                    if (x != x) anynan = true; else val = x;
-                }
-            }
-            v[k++] = val;
-        }
-    }
-    if (ngood < min_valid) return false;
-    if (anynan) { result = NAN; return true; }
-    sort_donors<NV>(v);
-    float a = pick<NV>(v, (ngood - 1) >> 1);
-    float b = pick<NV>(v, ngood >> 1);
-    result = (ngood & 1) ? a : __fmul_rn(__fadd_rn(a, b), 0.5f);
-    return true;
-}
 
 // Any deltapix up to 7: donors in local memory, insertion sort.
 template <typename MaskT>
@@ -111,46 +59,107 @@ __device__ __noinline__ bool repair_any(const float* __restrict__ data, const Ma
 
 constexpr int BP_THREADS = 256;
 
-// grid.x covers the 4-pixel groups of one row, grid.y the rows of the band.
+// Warp-cooperative median of the good neighbours of bad pixel (r, c), DP in {1, 2}:
+// lane l fetches neighbour l of the (2*DP+1)^2 window, the 32 lanes sort their
+// values with a bitonic network of shuffles (+inf for non-donors), and the middle
+// order statistics are read back by shuffle.  ~80 warp instructions per bad pixel
+// instead of a ~700-instruction single-lane detour that idles the other 31 lanes.
+template <int DP, typename MaskT>
+__device__ __forceinline__ bool repair_warp(const float* __restrict__ data, const MaskT* __restrict__ mask,
+                                            int64_t H, int64_t W, int64_t band_row0,
+                                            int64_t r, int64_t c, int min_valid, float& result) {
+    constexpr int WD = 2 * DP + 1;
+    const int lane = threadIdx.x & 31;
+    const int dr = lane / WD - DP, dc = lane % WD - DP;
+    float v = INFINITY;
+    bool good = false, isnan_ = false;
+    if (lane < WD * WD && !(dr == 0 && dc == 0)) {
+        const int64_t rr = r + dr, cc = c + dc;
+        if (rr >= 0 && rr < H && cc >= 0 && cc < W) {
+            const int64_t idx = (rr - band_row0) * W + cc;
+            if (!mask_bad(mask, idx)) {
+                const float x = data[idx];
+                good = true;
+                if (x != x) isnan_ = true; else v = x;
+            }
+        }
+    }
+    const int ngood = __popc(__ballot_sync(0xffffffffu, good));
+    const bool anynan = __ballot_sync(0xffffffffu, isnan_) != 0u;
+    if (ngood < min_valid) return false;
+    if (anynan) { result = NAN; return true; }
+    // bitonic sort, ascending across lanes
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const float o = __shfl_xor_sync(0xffffffffu, v, j);
+            const bool up = ((lane & k) == 0);            // ascending block
+            const bool lower = ((lane & j) == 0);
+            v = (up == lower) ? fminf(v, o) : fmaxf(v, o);
+        }
+    }
+    const float a = __shfl_sync(0xffffffffu, v, (ngood - 1) >> 1);
+    const float b = __shfl_sync(0xffffffffu, v, ngood >> 1);
+    result = (ngood & 1) ? a : __fmul_rn(__fadd_rn(a, b), 0.5f);
+    return true;
+}
+
+// grid.x covers the 4-pixel groups of one row (whole warps), grid.y the rows of the band.
 template <int DP, typename MaskT>
 __global__ void __launch_bounds__(BP_THREADS)
 fix_badpix_kernel(const float* __restrict__ data, const MaskT* __restrict__ mask,
                   int64_t H, int64_t W, int64_t band_row0, int64_t row0, int64_t nrows,
                   int dp, int min_valid, float* __restrict__ out,
                   unsigned long long* __restrict__ counts, bool vec_ok) {
-    int64_t groups_per_row = (W + 3) / 4;
-    int64_t g = (int64_t)blockIdx.x * BP_THREADS + threadIdx.x;
+    const int64_t groups_per_row = (W + 3) / 4;
+    const int64_t g = (int64_t)blockIdx.x * BP_THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    // whole warps stay in the loop together (a warp whose first group is past the row leaves as one)
+    const bool warp_active = (g - lane) < groups_per_row;
     unsigned nbad = 0, nfix = 0;
-    for (int64_t rel = blockIdx.y; rel < nrows; rel += gridDim.y) {
-        if (g >= groups_per_row) break;
-        int64_t r = row0 + rel;
-        int64_t c0 = g * 4;
-        int64_t in_base = (r - band_row0) * W + c0;
-        int64_t out_base = rel * W + c0;
-        float px[4];
-        bool bad[4];
-        int nvalid = (int)((W - c0) < 4 ? (W - c0) : 4);
+    for (int64_t rel = blockIdx.y; warp_active && rel < nrows; rel += gridDim.y) {
+        const int64_t r = row0 + rel;
+        const int64_t c0 = g * 4;
+        const int64_t in_base = (r - band_row0) * W + c0;
+        const int64_t out_base = rel * W + c0;
+        float px[4] = {0.f, 0.f, 0.f, 0.f};
+        bool bad[4] = {false, false, false, false};
+        const int nvalid = g < groups_per_row ? (int)((W - c0) < 4 ? (W - c0) : 4) : 0;
         if (vec_ok && nvalid == 4) {
-            float4 d = ld_stream(reinterpret_cast<const float4*>(data + in_base));
+            const float4 d = ld_stream(reinterpret_cast<const float4*>(data + in_base));
             px[0] = d.x; px[1] = d.y; px[2] = d.z; px[3] = d.w;
+            if (sizeof(MaskT) == 1) {
+                const uchar4 m4 = __ldcs(reinterpret_cast<const uchar4*>(mask + in_base));
+                bad[0] = m4.x != 0; bad[1] = m4.y != 0; bad[2] = m4.z != 0; bad[3] = m4.w != 0;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) bad[k] = mask_bad(mask, in_base + k);
+            }
         } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) px[k] = (k < nvalid) ? data[in_base + k] : 0.f;
+            for (int k = 0; k < 4; ++k) {
+                if (k < nvalid) { px[k] = data[in_base + k]; bad[k] = mask_bad(mask, in_base + k); }
+            }
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) bad[k] = (k < nvalid) && mask_bad(mask, in_base + k);
-#pragma unroll
         for (int k = 0; k < 4; ++k) {
-            if (bad[k]) {
+            if (DP == 1 || DP == 2) {
+                unsigned todo = __ballot_sync(0xffffffffu, bad[k]);
+                nbad += bad[k] ? 1u : 0u;
+                while (todo) {
+                    const int src = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int64_t cc = __shfl_sync(0xffffffffu, c0, src) + k;
+                    float res = 0.f;
+                    const bool ok = repair_warp<(DP == 1 || DP == 2) ? DP : 1, MaskT>(
+                        data, mask, H, W, band_row0, r, cc, min_valid, res);
+                    if (ok && lane == src) { px[k] = res; ++nfix; }
+                }
+            } else if (bad[k]) {
                 ++nbad;
                 float res;
-                bool ok;
-                if (DP == 1 || DP == 2)
-                    ok = repair_small<(DP == 1 || DP == 2) ? DP : 1, MaskT>(
-                        data, mask, H, W, band_row0, r, c0 + k, min_valid, res);
-                else
-                    ok = repair_any<MaskT>(data, mask, H, W, band_row0, r, c0 + k, dp, min_valid, res);
-                if (ok) { px[k] = res; ++nfix; }
+                if (repair_any<MaskT>(data, mask, H, W, band_row0, r, c0 + k, dp, min_valid, res)) { px[k] = res; ++nfix; }
             }
         }
         if (vec_ok && nvalid == 4) {
@@ -165,7 +174,7 @@ fix_badpix_kernel(const float* __restrict__ data, const MaskT* __restrict__ mask
         nbad += __shfl_down_sync(0xffffffffu, nbad, off);
         nfix += __shfl_down_sync(0xffffffffu, nfix, off);
     }
-    if ((threadIdx.x & 31) == 0 && nbad) {
+    if (lane == 0 && nbad) {
         atomicAdd(&counts[0], (unsigned long long)nbad);
         if (nfix) atomicAdd(&counts[1], (unsigned long long)nfix);
     }
@@ -178,7 +187,7 @@ int launch_bp(const float* data, const MaskT* mask, int64_t H, int64_t W, int64_
     int64_t groups = (W + 3) / 4;
     dim3 grid((unsigned)((groups + BP_THREADS - 1) / BP_THREADS),
               (unsigned)(nrows < 65535 ? nrows : 65535));
-    bool vec_ok = (W % 4 == 0) && apgpu_aligned(data, 16) && apgpu_aligned(out, 16);
+    bool vec_ok = (W % 4 == 0) && apgpu_aligned(data, 16) && apgpu_aligned(out, 16) && apgpu_aligned(mask, 4);
     unsigned long long* c = reinterpret_cast<unsigned long long*>(counts);
     if (dp == 1)
         fix_badpix_kernel<1, MaskT><<<grid, BP_THREADS, 0, st>>>(data, mask, H, W, band_row0, row0, nrows, dp, min_valid, out, c, vec_ok);
