@@ -782,23 +782,29 @@ stack_sorted_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_const
 #pragma unroll
     for (int i = 0; i < NB; ++i) s[i * TPB] = x[i];
     const int base = nneg;               // real samples occupy rows [base, base + N)
-    // MAD by two-pointer merge outwards from the median (float64, exact).
-    int l = base + ((N - 1) >> 1), r = l + 1;
-    const int k1 = (N - 1) >> 1, k2 = N >> 1;
-    double d1 = 0.0, d2 = 0.0;
-    double dl = fabs(__dsub_rn((double)s[l * TPB], med));
-    double dr = fabs(__dsub_rn((double)s[r * TPB], med));
-    for (int t = 0; t <= k2; ++t) {
-        const bool left = dl <= dr;
-        const double d = left ? dl : dr;
-        l -= left ? 1 : 0;
-        r += left ? 0 : 1;
-        const double dn = fabs(__dsub_rn((double)s[(left ? l : r) * TPB], med));
-        dl = left ? dn : dl;
-        dr = left ? dr : dn;
-        if (t == k1) d1 = d;
-        if (t == k2) d2 = d;
+    // MAD = median of |x - med|.  Left of the median the deviations grow towards row
+    // `base`, right of it towards row `base+N`: two sorted lists,
+    //     L[j] = med - s[l0 - j]   (j = 0 .. nL-1),   R[j] = s[l0 + 1 + j] - med   (j = 0 .. nR-1),
+    // whose (k+1)-th smallest element is found by bisecting on how many come from L
+    // (O(log N) shared-memory reads, float64, exact).  Guard rows / +-inf padding give
+    // every out-of-range index an infinite deviation.
+    const int l0 = base + ((N - 1) >> 1);
+    const int nL = l0 - base + 1, nR = N - nL;
+    auto devL = [&](int j) { return fabs(__dsub_rn((double)s[(l0 - j) * TPB], med)); };
+    auto devR = [&](int j) { return fabs(__dsub_rn((double)s[(l0 + 1 + j) * TPB], med)); };
+    const int k1 = (N - 1) >> 1;                       // 0-based rank of the lower middle deviation
+    int lo_i = k1 + 1 - nR > 0 ? k1 + 1 - nR : 0;
+    int hi_i = k1 + 1 < nL ? k1 + 1 : nL;
+    while (lo_i < hi_i) {
+        const int mid = (lo_i + hi_i) >> 1;
+        if (devL(mid) < devR(k1 - mid)) lo_i = mid + 1; else hi_i = mid;
     }
+    // lo_i samples of the k1+1 smallest deviations come from L, k1+1-lo_i from R
+    const double la = lo_i > 0 ? devL(lo_i - 1) : -1.0;
+    const double ra = (k1 - lo_i) >= 0 ? devR(k1 - lo_i) : -1.0;
+    const double d1 = la > ra ? la : ra;
+    const double lb = devL(lo_i), rb = devR(k1 + 1 - lo_i);      // the next deviation up (inf past the ends)
+    const double d2 = lb < rb ? lb : rb;
     const double mad = (N & 1) ? d1 : __dmul_rn(__dadd_rn(d1, d2), 0.5);
     const double sd = __dmul_rn(MAD_TO_STD, mad);
     const double lo = __dsub_rn(med, __dmul_rn(sd, a.klo));
