@@ -187,6 +187,16 @@ def run_reference(args, shape):
     print(json.dumps(line))
 
 
+def recorded_traffic(kname, shape):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (or None)."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f)["traffic_bytes"].get(f"{kname}@{shape['n']}x{shape['h']}x{shape['w']}")
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def workload_name(shape):
     return f"kappa-sigma-clipped mean stack {shape['n']}x({shape['w']}x{shape['h']}) float32"
 
@@ -361,7 +371,7 @@ def run_gpu(args, shape):
                        "per_gpu": f"{n}x({w}x{h})", "l2": "inputs (24.5 GB/GPU) >> L2 (126 MB): no flush needed"},
             "clocks": clocks, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / hbm_peak, "traffic": recorded_traffic(kname, shape), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel": kname},
             "e2e": e2e, "cpu_baseline": cpu, "variants": variants,
         }

@@ -30,7 +30,10 @@ STALL = "smsp__average_warps_issue_stalled_"
 
 def main():
     rep = sys.argv[1]
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):          # a raw page already exported on the GPU box
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     for r in rows[2:]:
