@@ -311,12 +311,11 @@ __device__ __forceinline__ void meanclip_pixel(float2 (&y)[NB / 2], const FrameP
         if (!(ylo_in < 0.f && yhi_in > 0.f)) { uncertain = true; break; }
         const float2 negc = make_float2(-c, -c);
         const int nk_before = nk;
-        float n1 = 0.f, n2 = 0.f;
         uint64_t flags = 0;              // bit g: group g holds a sample outside the inner bounds
-        // common pass: tight straight-line code, no per-sample predicates
+        // test pass: tight straight-line code, no per-sample predicates, no sums (the sums of
+        // the survivors only change when something is rejected)
 #pragma unroll
         for (int gidx = 0; gidx < NG; ++gidx) {
-            float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
             float tmax = 0.f, tmin = 0.f;
 #pragma unroll
             for (int k = 0; k < GP; ++k) {
@@ -329,46 +328,51 @@ __device__ __forceinline__ void meanclip_pixel(float2 (&y)[NB / 2], const FrameP
                         tmax = fmaxf(tmax, fmaxf(t.x, t.y));
                         tmin = fminf(tmin, fminf(t.x, t.y));
                     }
-                    s1 = __fadd2_rn(s1, y[j]);
-                    s2 = __ffma2_rn(y[j], y[j], s2);
                 }
             }
             const bool flagged = SYM ? (tmax >= t_in) : (tmax >= hi_in || tmin <= lo_in);
-            if (flagged) {
-                flags |= (uint64_t)1 << gidx;
+            if (flagged) flags |= (uint64_t)1 << gidx;
+        }
+        if (flags == 0) break;           // every survivor is certainly inside the bounds: converged
+        // update pass: flagged groups sample by sample, the others with packed sums
+        float n1 = 0.f, n2 = 0.f;
+#pragma unroll
+        for (int gidx = 0; gidx < NG; ++gidx) {
+            if ((flags >> gidx) & 1) {
+                float g1 = 0.f, g2 = 0.f, vmax = 0.f, vmin = 0.f;
+#pragma unroll
+                for (int k = 0; k < 2 * GP; ++k) {
+                    const int i = gidx * 2 * GP + k;
+                    if (i < NB) {
+                        // compare y against bounds shifted by c (not t = y - c: keeps the
+                        // compiler from holding every t of the test pass live in registers)
+                        float v = (i & 1) ? y[i >> 1].y : y[i >> 1].x;
+                        const bool keep = (v >= ylo_out) && (v <= yhi_out);
+                        nk -= keep ? 0 : 1;                      // certainly rejected
+                        v = keep ? v : 0.f;
+                        if (i & 1) y[i >> 1].y = v; else y[i >> 1].x = v;
+                        vmax = fmaxf(vmax, v);
+                        vmin = fminf(vmin, v);
+                        g1 += v;
+                        g2 = fmaf(v, v, g2);
+                    }
+                }
+                // a survivor inside the guard band: float64 must decide
+                if (!(vmin > ylo_in && vmax < yhi_in)) uncertain = true;
+                n1 += g1;
+                n2 += g2;
             } else {
+                float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < GP; ++k) {
+                    const int j = gidx * GP + k;
+                    if (j < NP) {
+                        s1 = __fadd2_rn(s1, y[j]);
+                        s2 = __ffma2_rn(y[j], y[j], s2);
+                    }
+                }
                 n1 += s1.x + s1.y;
                 n2 += s2.x + s2.y;
-            }
-        }
-        // rare pass: only the flagged groups, sample by sample
-        if (flags) {
-#pragma unroll
-            for (int gidx = 0; gidx < NG; ++gidx) {
-                if ((flags >> gidx) & 1) {
-                    float g1 = 0.f, g2 = 0.f, vmax = 0.f, vmin = 0.f;
-#pragma unroll
-                    for (int k = 0; k < 2 * GP; ++k) {
-                        const int i = gidx * 2 * GP + k;
-                        if (i < NB) {
-                            // compare y against bounds shifted by c (not t = y - c: keeps the
-                            // compiler from holding every t of the common pass live in registers)
-                            float v = (i & 1) ? y[i >> 1].y : y[i >> 1].x;
-                            const bool keep = (v >= ylo_out) && (v <= yhi_out);
-                            nk -= keep ? 0 : 1;                      // certainly rejected
-                            v = keep ? v : 0.f;
-                            if (i & 1) y[i >> 1].y = v; else y[i >> 1].x = v;
-                            vmax = fmaxf(vmax, v);
-                            vmin = fminf(vmin, v);
-                            g1 += v;
-                            g2 = fmaf(v, v, g2);
-                        }
-                    }
-                    // a survivor inside the guard band: float64 must decide
-                    if (!(vmin > ylo_in && vmax < yhi_in)) uncertain = true;
-                    n1 += g1;
-                    n2 += g2;
-                }
             }
         }
         if (uncertain) break;
