@@ -719,25 +719,35 @@ stack_meanclip_smem_kernel(const __grid_constant__ FramePtrs<CAP> fp, const __gr
 // ---------------------------------------------------------------------------
 // sorted<NB, NLO, MODE>: Batcher network in registers, N in (NLO, NB]
 // ---------------------------------------------------------------------------
+constexpr int STPB = 256;         // threads per CTA of the sorted kernels (lock-stepped, see sort_regs)
 constexpr int MODE_MED = 0;       // method=median, no clipping
 constexpr int MODE_MEDMAD1 = 1;   // one median/MAD clip pass, then the mean (ApMasterCal)
 
 #define CE_X(i, j) { float lo_ = fminf(x[i], x[j]); float hi_ = fmaxf(x[i], x[j]); x[i] = lo_; x[j] = hi_; }
 
+// Every 128 comparators the network has a CTA barrier: the 8 warps of a CTA walk the ~35 KB of
+// straight-line code together, so one instruction-cache fill serves all of them (ncu before:
+// `no_instruction` was the top stall of the median/MAD kernel).  The network is branch-free
+// and data-independent, so the barrier costs no load imbalance.
+#define SY_X() __syncthreads();
 template <int NB> __device__ __forceinline__ void sort_regs(float (&x)[NB]);
 #define APGPU_DEF_SORT(n) \
-    template <> __device__ __forceinline__ void sort_regs<n>(float (&x)[n]) { APGPU_SORTNET_##n(CE_X) }
+    template <> __device__ __forceinline__ void sort_regs<n>(float (&x)[n]) { APGPU_SORTNET_##n(CE_X, SY_X) }
 APGPU_DEF_SORT(4) APGPU_DEF_SORT(8) APGPU_DEF_SORT(12) APGPU_DEF_SORT(16) APGPU_DEF_SORT(20)
 APGPU_DEF_SORT(24) APGPU_DEF_SORT(32) APGPU_DEF_SORT(40) APGPU_DEF_SORT(48) APGPU_DEF_SORT(56)
 APGPU_DEF_SORT(64) APGPU_DEF_SORT(72) APGPU_DEF_SORT(80) APGPU_DEF_SORT(90) APGPU_DEF_SORT(100)
 APGPU_DEF_SORT(112) APGPU_DEF_SORT(128)
 
 template <int NB, int NLO, int MODE>
-__global__ void __launch_bounds__(TPB)
+__global__ void __launch_bounds__(STPB, (NB <= 32 ? 4 : (NB <= 100 ? 2 : 1)))
 stack_sorted_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_constant__ StackArgs a) {
     extern __shared__ float col[];       // MODE_MEDMAD1: [NB + 2][TPB] sorted columns + guard rows
-    const int64_t p = a.pix0 + (int64_t)blockIdx.x * TPB + threadIdx.x;
-    if (p >= a.pix0 + a.npix) return;
+    // no early exit: the sort contains CTA barriers.  Threads past the end redo the last pixel
+    // and skip the write.
+    const int64_t pend = a.pix0 + a.npix;
+    int64_t p = a.pix0 + (int64_t)blockIdx.x * STPB + threadIdx.x;
+    const bool valid = p < pend;
+    if (!valid) p = pend - 1;
     const int N = a.N;
     // Pad to NB with -inf / +inf split so that the real samples sit centred in
     // the sorted array: the median is then at the compile-time index NB/2-1
@@ -763,9 +773,11 @@ stack_sorted_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_const
             if (MODE == MODE_MEDMAD1) sum_all = __dadd_rn(sum_all, (double)x[i]);   // frame order, as nanmean
         }
     }
-    if (z != z) { generic_pixel<NB>(fp, a, p); return; }
+    const bool nonfinite = (z != z);          // handled after the (barrier-carrying) sort
 
     sort_regs<NB>(x);
+    if (!valid) return;
+    if (nonfinite) { generic_pixel<NB>(fp, a, p); return; }
 
     constexpr int C = NB / 2;
     const double med = (N & 1) ? (double)x[C - 1]
@@ -780,11 +792,11 @@ stack_sorted_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_const
     // and row NB+1 are -inf / +inf guards, so together with the +-inf padding
     // every row outside the real samples has an infinite deviation from the
     // median and the merge below needs no bounds checks.
-    float* s = col + threadIdx.x + TPB;          // s[i * TPB] = sorted sample i, i in [-1, NB]
-    s[-TPB] = -INFINITY;
-    s[NB * TPB] = INFINITY;
+    float* s = col + threadIdx.x + STPB;          // s[i * STPB] = sorted sample i, i in [-1, NB]
+    s[-STPB] = -INFINITY;
+    s[NB * STPB] = INFINITY;
 #pragma unroll
-    for (int i = 0; i < NB; ++i) s[i * TPB] = x[i];
+    for (int i = 0; i < NB; ++i) s[i * STPB] = x[i];
     const int base = nneg;               // real samples occupy rows [base, base + N)
     // MAD = median of |x - med|.  Left of the median the deviations grow towards row
     // `base`, right of it towards row `base+N`: two sorted lists,
@@ -794,8 +806,8 @@ stack_sorted_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_const
     // every out-of-range index an infinite deviation.
     const int l0 = base + ((N - 1) >> 1);
     const int nL = l0 - base + 1, nR = N - nL;
-    auto devL = [&](int j) { return fabs(__dsub_rn((double)s[(l0 - j) * TPB], med)); };
-    auto devR = [&](int j) { return fabs(__dsub_rn((double)s[(l0 + 1 + j) * TPB], med)); };
+    auto devL = [&](int j) { return fabs(__dsub_rn((double)s[(l0 - j) * STPB], med)); };
+    auto devR = [&](int j) { return fabs(__dsub_rn((double)s[(l0 + 1 + j) * STPB], med)); };
     const int k1 = (N - 1) >> 1;                       // 0-based rank of the lower middle deviation
     int lo_i = k1 + 1 - nR > 0 ? k1 + 1 - nR : 0;
     int hi_i = k1 + 1 < nL ? k1 + 1 : nL;
@@ -814,8 +826,8 @@ stack_sorted_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_const
     const double lo = __dsub_rn(med, __dmul_rn(sd, a.klo));
     const double hi = __dadd_rn(med, __dmul_rn(sd, a.khi));
     int sa = base, sb = base + N;
-    while (sa < sb && (double)s[sa * TPB] < lo) ++sa;
-    while (sa < sb && (double)s[(sb - 1) * TPB] > hi) --sb;
+    while (sa < sb && (double)s[sa * STPB] < lo) ++sa;
+    while (sa < sb && (double)s[(sb - 1) * STPB] > hi) --sb;
     const int nk = sb - sa;
 #ifdef APGPU_DEBUG_MEDMAD
     if (p == a.pix0) printf("dbg N=%d NB=%d base=%d med=%.6f d1=%.6f d2=%.6f mad=%.6f lo=%.6f hi=%.6f sa=%d sb=%d klo=%f\n",
@@ -826,14 +838,14 @@ stack_sorted_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_const
         mean = __ddiv_rn(sum_all, (double)N);
     } else {
         double acc = 0.0;
-        for (int i = sa; i < sb; ++i) acc = __dadd_rn(acc, (double)s[i * TPB]);
+        for (int i = sa; i < sb; ++i) acc = __dadd_rn(acc, (double)s[i * STPB]);
         mean = __ddiv_rn(acc, (double)nk);      // nk >= 1: the median itself always survives
     }
     double unc = (double)NAN;
     if (a.uncert) {
         double acc = 0.0;
         for (int i = sa; i < sb; ++i) {
-            double d = __dsub_rn((double)s[i * TPB], mean);
+            double d = __dsub_rn((double)s[i * STPB], mean);
             acc = __dadd_rn(acc, __dmul_rn(d, d));
         }
         unc = __ddiv_rn(__dsqrt_rn(__ddiv_rn(acc, (double)nk)), __dsqrt_rn((double)nk));
@@ -962,12 +974,12 @@ template <int NB, int NLO, int MODE>
 int launch_sorted(const float* const* frames, const StackArgs& a, cudaStream_t st) {
     FramePtrs<NB> fp;
     for (int i = 0; i < NB; ++i) fp.p[i] = i < a.N ? frames[i] : nullptr;
-    int64_t blocks = (a.npix + TPB - 1) / TPB;
-    size_t smem = (MODE == MODE_MEDMAD1) ? (size_t)(NB + 2) * TPB * sizeof(float) : 0;
+    int64_t blocks = (a.npix + STPB - 1) / STPB;
+    size_t smem = (MODE == MODE_MEDMAD1) ? (size_t)(NB + 2) * STPB * sizeof(float) : 0;
     if (smem > 48 * 1024)
         APGPU_CUDA(cudaFuncSetAttribute(stack_sorted_kernel<NB, NLO, MODE>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    stack_sorted_kernel<NB, NLO, MODE><<<(unsigned)blocks, TPB, smem, st>>>(fp, a);
+    stack_sorted_kernel<NB, NLO, MODE><<<(unsigned)blocks, STPB, smem, st>>>(fp, a);
     APGPU_LAUNCH_CHECK("stack_sorted_kernel");
     return APGPU_OK;
 }
