@@ -39,6 +39,7 @@ namespace {
 constexpr double MAD_TO_STD = 1.482602218505602;   // astropy.stats.mad_std scale
 constexpr int TPB = 128;                           // threads (= pixels) per block
 constexpr int SMEM_MAX_BYTES = 227 * 1024;         // opt-in dynamic shared memory per CTA / per SM budget
+constexpr int MEANCLIP_MAX_TAIL = 40;              // widest meanclip bucket (160, 200]
 
 struct StackArgs {
     int N, method, maxiters, cen, dev;
@@ -48,6 +49,11 @@ struct StackArgs {
     void* nrej; int nrej_u16;
     void* uncert;
     uint8_t* allmasked;
+    // meanclip<NB, NLO>: 1.0f for a real frame, 0.0f for padding, for frames NLO .. NB-1.  The
+    // kernels load the padding slots unconditionally (the host points them at frame 0, the
+    // staged kernels zero the rows) and multiply the pivot-shifted value by this mask: no
+    // per-sample predicates in the load phase.
+    float tailmask[MEANCLIP_MAX_TAIL];
 };
 
 template <int CAP> struct FramePtrs { const float* p[CAP]; };
@@ -268,8 +274,8 @@ __device__ __forceinline__ void meanclip_pixel(float2 (&y)[NB / 2], const FrameP
             const int j = gidx * GP + k;
             if (j < NP) {
                 float2 d = __fadd2_rn(y[j], negpiv);
-                if (!APGPU_ACTIVE(2 * j)) d.x = 0.f;       // padding beyond N (compile-time false below NLO)
-                if (!APGPU_ACTIVE(2 * j + 1)) d.y = 0.f;
+                if (2 * j >= NLO)                          // bucket tail: padding beyond N becomes y = 0
+                    d = __fmul2_rn(d, make_float2(a.tailmask[2 * j - NLO], a.tailmask[2 * j + 1 - NLO]));
                 y[j] = d;
                 s1 = __fadd2_rn(s1, d);
                 s2 = __ffma2_rn(d, d, s2);
@@ -414,13 +420,12 @@ __global__ void __launch_bounds__(TPB, meanclip_min_blocks(NB))
 stack_meanclip_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_constant__ StackArgs a) {
     const int64_t p = a.pix0 + (int64_t)blockIdx.x * TPB + threadIdx.x;
     if (p >= a.pix0 + a.npix) return;
-    const int N = a.N;
     const uint32_t p32 = (uint32_t)p;                  // host guarantees H*W < 2^32
     float2 y[NB / 2];
 #pragma unroll
-    for (int j = 0; j < NB / 2; ++j) {
-        y[j].x = APGPU_ACTIVE(2 * j) ? ld_stream(fp.p[2 * j] + p32) : 0.f;
-        y[j].y = APGPU_ACTIVE(2 * j + 1) ? ld_stream(fp.p[2 * j + 1] + p32) : 0.f;
+    for (int j = 0; j < NB / 2; ++j) {                 // padding slots point at frame 0 (masked later)
+        y[j].x = ld_stream(fp.p[2 * j] + p32);
+        y[j].y = ld_stream(fp.p[2 * j + 1] + p32);
     }
     meanclip_pixel<NB, NLO, SYM>(y, fp, a, p);
 }
@@ -488,6 +493,7 @@ stack_meanclip_tma_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid
     const int N = a.N;
     const int64_t ntiles = a.npix / TTPB;                                    // full tiles only (host launches the tail)
     if (threadIdx.x == 0) mbar_init(bar, 1);
+    for (int i = N * TTPB + threadIdx.x; i < NB * TTPB; i += TTPB) stage[i] = 0.f;   // padding rows: never copied into
     __syncthreads();
     int64_t tile = blockIdx.x;
     uint32_t parity = 0;
@@ -498,8 +504,8 @@ stack_meanclip_tma_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid
         float2 y[NB / 2];
 #pragma unroll
         for (int j = 0; j < NB / 2; ++j) {
-            y[j].x = APGPU_ACTIVE(2 * j) ? stage[(2 * j) * TTPB + threadIdx.x] : 0.f;
-            y[j].y = APGPU_ACTIVE(2 * j + 1) ? stage[(2 * j + 1) * TTPB + threadIdx.x] : 0.f;
+            y[j].x = stage[(2 * j) * TTPB + threadIdx.x];
+            y[j].y = stage[(2 * j + 1) * TTPB + threadIdx.x];
         }
         __syncthreads();                                                     // every thread has drained the stage
         const int64_t next = tile + gridDim.x;
@@ -547,6 +553,7 @@ stack_meanclip_cpasync_kernel(const __grid_constant__ FramePtrs<NB> fp, const __
     float* stage = reinterpret_cast<float*>(smem_raw + (size_t)NB * sizeof(float*)) + (size_t)warp * NB * WT;
     const int N = a.N;
     for (int i = threadIdx.x; i < N; i += TPB) ptab[i] = fp.p[i];
+    for (int i = N * WT + lane; i < NB * WT; i += 32) stage[i] = 0.f;         // padding rows: never copied into
     __syncthreads();
     const int64_t ntiles = a.npix / WT;                                       // full warp tiles (host launches the tail)
     const int64_t nwarps = (int64_t)gridDim.x * (TPB / 32);
@@ -558,8 +565,8 @@ stack_meanclip_cpasync_kernel(const __grid_constant__ FramePtrs<NB> fp, const __
         float2 y[NB / 2];
 #pragma unroll
         for (int j = 0; j < NB / 2; ++j) {
-            y[j].x = APGPU_ACTIVE(2 * j) ? stage[(2 * j) * WT + lane] : 0.f;
-            y[j].y = APGPU_ACTIVE(2 * j + 1) ? stage[(2 * j + 1) * WT + lane] : 0.f;
+            y[j].x = stage[(2 * j) * WT + lane];
+            y[j].y = stage[(2 * j + 1) * WT + lane];
         }
         __syncwarp();                                                         // stage drained by every lane
         const int64_t next = tile + nwarps;
@@ -953,9 +960,12 @@ int launch_meanclip_sym(const FramePtrs<NB>& fp, const StackArgs& a, int staging
 }
 
 template <int NB, int NLO>
-int launch_meanclip(const float* const* frames, const StackArgs& a, cudaStream_t st, int flags) {
+int launch_meanclip(const float* const* frames, const StackArgs& a_in, cudaStream_t st, int flags) {
+    static_assert(NB - NLO <= MEANCLIP_MAX_TAIL, "tail mask too small");
     FramePtrs<NB> fp;
-    for (int i = 0; i < NB; ++i) fp.p[i] = i < a.N ? frames[i] : nullptr;
+    for (int i = 0; i < NB; ++i) fp.p[i] = i < a_in.N ? frames[i] : frames[0];   // padding: loaded, then masked
+    StackArgs a = a_in;
+    for (int i = NLO; i < NB; ++i) a.tailmask[i - NLO] = i < a.N ? 1.f : 0.f;
     // asynchronous copies need 16-byte aligned sources: frame base + first pixel of the band
     // default (measured, bench.py variants): the warp-granular cp.async pipeline wins for the
     // shorter stacks (N=30: +8 %), direct loads are level or slightly ahead from N~80 up
