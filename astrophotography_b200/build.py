@@ -21,7 +21,9 @@ INCLUDE = os.path.join(ROOT, "include")
 BUILD_DIR = os.path.join(PKG_DIR, "_build")
 LIB_PATH = os.path.join(PKG_DIR, "libapgpu.so")
 
-SOURCES = ["apgpu_core.cu", "calibrate.cu", "badpix.cu", "stack.cu", "stats.cu"]
+SOURCES = ["stack_meanclip_mid.cu", "stack_meanclip_hi.cu", "stack_meanclip_lo.cu", "stack_sorted_medmad1.cu",
+           "stack_sorted_med.cu", "stack_meanclip_smem.cu", "stack_generic.cu", "stack.cu",
+           "apgpu_core.cu", "calibrate.cu", "badpix.cu", "stats.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

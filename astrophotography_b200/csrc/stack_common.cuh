@@ -1,0 +1,257 @@
+// Frame-stack reducer (sm_100a): per-pixel median / sigma-clipped mean over N frames.
+//
+// Replaces ccdproc.combine(...) as called by the reference at
+// AstroPhotography/scripts/ap_combine_darks.py:411-420 (settings :394-399) and
+// generalises it to astropy.stats.sigma_clip's iterative kappa-sigma clip.
+//
+// Layout: N separate H x W float32 frames (frame-major; never transposed in
+// HBM).  One thread owns one pixel; a warp reads 128 contiguous bytes of each
+// frame, so every HBM access is a full coalesced line and each input byte is
+// read exactly once (4*N + 5 B per pixel algorithmic traffic).
+//
+// Three kernel families behind one entry point:
+//   generic<CAP>      every parameter combination, N <= 1024.  float64
+//                     arithmetic in the oracle's operation order (explicitly
+//                     rounded intrinsics, no FMA contraction): bit-identical to
+//                     the numpy restatement.  Values live in local memory.
+//   meanclip<NB,NLO>  iterative kappa-sigma clip about the MEAN with the
+//                     population STD, then the mean of the survivors.
+//                     Register-resident (N <= 200), float32 arithmetic on
+//                     pivot-shifted values with a rigorous error bound: a pixel
+//                     whose decision could differ from the float64 oracle
+//                     (a sample within the bound of a clip threshold) is redone
+//                     by the generic routine, so rejection maps are identical.
+//   sorted<NB,MODE>   register-resident Batcher merge-exchange network
+//                     (N <= 128): plain median (MODE_MED), or the reference's
+//                     ApMasterCal setting -- one median/MAD clip pass then the
+//                     mean (MODE_MEDMAD1) -- with the sorted column parked in
+//                     shared memory for the data-dependent MAD selection.
+//   A pixel holding NaN/inf samples leaves the fast kernels for the generic
+//   routine, which owns the reference's non-finite semantics.
+#pragma once
+#include <float.h>
+#include <math.h>
+
+#include "apgpu_common.cuh"
+
+namespace apgpu_stack {
+
+constexpr double MAD_TO_STD = 1.482602218505602;   // astropy.stats.mad_std scale
+constexpr int TPB = 128;                           // threads (= pixels) per block
+constexpr int SMEM_MAX_BYTES = 227 * 1024;         // opt-in dynamic shared memory per CTA / per SM budget
+constexpr int MEANCLIP_MAX_TAIL = 40;              // widest meanclip bucket (160, 200]
+
+struct StackArgs {
+    int N, method, maxiters, cen, dev;
+    double klo, khi;
+    int64_t pix0, npix;          // flat pixel range [pix0, pix0 + npix)
+    void* out; int out_f64;
+    void* nrej; int nrej_u16;
+    void* uncert;
+    uint8_t* allmasked;
+    // meanclip<NB, NLO>: 1.0f for a real frame, 0.0f for padding, for frames NLO .. NB-1.  The
+    // kernels load the padding slots unconditionally (the host points them at frame 0, the
+    // staged kernels zero the rows) and multiply the pivot-shifted value by this mask: no
+    // per-sample predicates in the load phase.
+    float tailmask[MEANCLIP_MAX_TAIL];
+};
+
+template <int CAP> struct FramePtrs { const float* p[CAP]; };
+
+__device__ __forceinline__ bool finite_f(float x) { return fabsf(x) <= FLT_MAX; }
+
+__device__ __forceinline__ void write_pixel(const StackArgs& a, int64_t p, double data, int nrej,
+                                            double unc, int allm) {
+    if (a.out_f64) reinterpret_cast<double*>(a.out)[p] = data;
+    else st_stream(reinterpret_cast<float*>(a.out) + p, (float)data);
+    if (a.nrej) {
+        if (a.nrej_u16) reinterpret_cast<uint16_t*>(a.nrej)[p] = (uint16_t)nrej;
+        else reinterpret_cast<uint8_t*>(a.nrej)[p] = (uint8_t)nrej;
+    }
+    if (a.uncert) {
+        if (a.out_f64) reinterpret_cast<double*>(a.uncert)[p] = unc;
+        else reinterpret_cast<float*>(a.uncert)[p] = (float)unc;
+    }
+    if (a.allmasked) a.allmasked[p] = (uint8_t)allm;
+}
+
+// ---------------------------------------------------------------------------
+// generic routine: float64, oracle operation order
+// ---------------------------------------------------------------------------
+static __device__ void shell_sort(float* s, int n) {
+    const int gaps[8] = {701, 301, 132, 57, 23, 10, 4, 1};
+    for (int g = 0; g < 8; ++g) {
+        int gap = gaps[g];
+        if (gap >= n && gap != 1) continue;
+        for (int i = gap; i < n; ++i) {
+            float t = s[i];
+            int j = i;
+            while (j >= gap && s[j - gap] > t) { s[j] = s[j - gap]; j -= gap; }
+            s[j] = t;
+        }
+    }
+}
+
+// median of the sorted range s[sa, sb): nanmedian's (lo + hi) / 2 in float64
+__device__ __forceinline__ double median_sorted(const float* s, int sa, int sb) {
+    int m = sb - sa;
+    if (m <= 0) return (double)NAN;
+    double lo = (double)s[sa + ((m - 1) >> 1)];
+    if (m & 1) return lo;
+    double hi = (double)s[sa + (m >> 1)];
+    return __dmul_rn(__dadd_rn(lo, hi), 0.5);
+}
+
+// median of |x - med| over the sorted range: the deviations left of the median
+// grow towards sa and those right of it grow towards sb, so the k-th smallest
+// comes out of a two-pointer merge -- no second sort.
+__device__ __forceinline__ double mad_sorted(const float* s, int sa, int sb, double med) {
+    int m = sb - sa;
+    if (m <= 0) return (double)NAN;
+    int l = sa + ((m - 1) >> 1), r = l + 1;
+    int k1 = (m - 1) >> 1, k2 = m >> 1;
+    double d1 = 0.0, d2 = 0.0;
+    for (int t = 0; t <= k2; ++t) {
+        double dl = (l >= sa) ? fabs(__dsub_rn((double)s[l], med)) : (double)INFINITY;
+        double dr = (r < sb) ? fabs(__dsub_rn((double)s[r], med)) : (double)INFINITY;
+        double d;
+        if (dl <= dr) { d = dl; --l; } else { d = dr; ++r; }
+        if (t == k1) d1 = d;
+        if (t == k2) d2 = d;
+    }
+    return (m & 1) ? d1 : __dmul_rn(__dadd_rn(d1, d2), 0.5);
+}
+
+template <int CAP>
+__device__ __noinline__ void generic_pixel(const FramePtrs<CAP>& fp, const StackArgs& a, int64_t p) {
+    float v[CAP];      // frame order; NaN marks a sample that is not (or no longer) used
+    float s[CAP];      // the used samples, ascending
+    const int N = a.N;
+    const bool clip = a.maxiters != 0;
+    const bool need_sorted = (a.method != APGPU_METHOD_AVERAGE) ||
+                             (clip && (a.cen == APGPU_CEN_MEDIAN || a.dev == APGPU_DEV_MAD_STD));
+    int nk = 0;
+    for (int i = 0; i < N; ++i) {
+        float x = ld_stream(fp.p[i] + p);
+        // sigma_clip rejects non-finite samples up front; without clipping the
+        // nan-functions only skip NaN.
+        bool ok = clip ? finite_f(x) : (x == x);
+        v[i] = ok ? x : NAN;
+        if (ok) { if (need_sorted) s[nk] = x; ++nk; }
+    }
+    if (need_sorted) shell_sort(s, nk);
+    int sa = 0, sb = nk;
+
+    auto mean_kept = [&](int cnt) -> double {          // np.nanmean: sequential sum / count
+        double acc = 0.0;
+        for (int i = 0; i < N; ++i) if (v[i] == v[i]) acc = __dadd_rn(acc, (double)v[i]);
+        return __ddiv_rn(acc, (double)cnt);
+    };
+    auto std_kept = [&](int cnt, double avg) -> double {   // np.nanstd, ddof=0
+        double acc = 0.0;
+        for (int i = 0; i < N; ++i)
+            if (v[i] == v[i]) { double d = __dsub_rn((double)v[i], avg); acc = __dadd_rn(acc, __dmul_rn(d, d)); }
+        return __dsqrt_rn(__ddiv_rn(acc, (double)cnt));
+    };
+
+    if (clip) {
+        int it = 0;
+        while (a.maxiters < 0 || it < a.maxiters) {
+            ++it;
+            if (nk == 0) break;
+            double avg = 0.0, med = 0.0;
+            if (a.cen == APGPU_CEN_MEAN || a.dev == APGPU_DEV_STD) avg = mean_kept(nk);
+            if (a.cen == APGPU_CEN_MEDIAN || a.dev == APGPU_DEV_MAD_STD) med = median_sorted(s, sa, sb);
+            double c = (a.cen == APGPU_CEN_MEAN) ? avg : med;
+            double sd = (a.dev == APGPU_DEV_STD) ? std_kept(nk, avg)
+                                                 : __dmul_rn(MAD_TO_STD, mad_sorted(s, sa, sb, med));
+            double lo = __dsub_rn(c, __dmul_rn(sd, a.klo));
+            double hi = __dadd_rn(c, __dmul_rn(sd, a.khi));
+            int changed = 0;
+            for (int i = 0; i < N; ++i) {
+                float x = v[i];
+                if (x == x && ((double)x < lo || (double)x > hi)) { v[i] = NAN; ++changed; }
+            }
+            if (need_sorted) {
+                while (sa < sb && (double)s[sa] < lo) ++sa;
+                while (sa < sb && (double)s[sb - 1] > hi) --sb;
+            }
+            nk -= changed;
+            if (changed == 0) break;
+        }
+    }
+
+    double data, unc = (double)NAN;
+    if (nk == 0) {
+        data = (double)NAN;
+    } else if (a.method == APGPU_METHOD_AVERAGE) {
+        data = mean_kept(nk);
+    } else if (a.method == APGPU_METHOD_MEDIAN) {
+        data = median_sorted(s, sa, sb);
+    } else if (a.method == APGPU_METHOD_MIN) {
+        data = (double)s[sa];
+    } else {
+        data = (double)s[sb - 1];
+    }
+    if (a.uncert && nk > 0) {
+        double dev;
+        if (a.method == APGPU_METHOD_MEDIAN) {
+            dev = __dmul_rn(MAD_TO_STD, mad_sorted(s, sa, sb, median_sorted(s, sa, sb)));
+        } else {
+            dev = std_kept(nk, mean_kept(nk));
+        }
+        unc = __ddiv_rn(dev, __dsqrt_rn((double)nk));
+    }
+    write_pixel(a, p, data, N - nk, unc, nk == 0);
+}
+
+
+// i < NLO is known at compile time to be a real frame; only the NB-NLO tail
+// elements carry a (warp-uniform) runtime predicate.
+#define APGPU_ACTIVE(i) ((i) < NLO || (i) < N)
+
+__device__ __forceinline__ float med3(float a, float b, float c) {
+    return fmaxf(fminf(a, b), fminf(fmaxf(a, b), c));
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* ptr) {
+    return (uint32_t)__cvta_generic_to_shared(ptr);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "APGPU_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra APGPU_DONE;\n"
+        "bra APGPU_WAIT;\n"
+        "APGPU_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// Threads (= pixels) per CTA of the TMA-staged kernel: 256, so that every bulk copy
+
+struct Bucket { int nb, nlo; };
+
+// cross-translation-unit launchers (one .cu per kernel family so that nvcc compiles them in parallel)
+int stack_launch_generic(const float* const* frames, const StackArgs& a, cudaStream_t st);
+int stack_dispatch_meanclip(int nb, const float* const* frames, const StackArgs& a, cudaStream_t st, int flags);
+int stack_dispatch_meanclip_lo(int nb, const float* const* frames, const StackArgs& a, cudaStream_t st, int flags);
+int stack_dispatch_meanclip_mid(int nb, const float* const* frames, const StackArgs& a, cudaStream_t st, int flags);
+int stack_dispatch_meanclip_hi(int nb, const float* const* frames, const StackArgs& a, cudaStream_t st, int flags);
+int stack_launch_meanclip_smem(const float* const* frames, const StackArgs& a, cudaStream_t st);
+int stack_dispatch_sorted_med(int nb, const float* const* frames, const StackArgs& a, cudaStream_t st);
+int stack_dispatch_sorted_medmad1(int nb, const float* const* frames, const StackArgs& a, cudaStream_t st);
+
+}  // namespace apgpu_stack

@@ -1,0 +1,401 @@
+// Frame-stack reducer: meanclip<NB, NLO> register-resident kappa-sigma kernels.  See stack_common.cuh.
+#pragma once
+#include "stack_common.cuh"
+
+namespace apgpu_stack {
+
+// ---------------------------------------------------------------------------
+// meanclip<NB, NLO>: kappa-sigma clip about the mean, N in (NLO, NB]
+// ---------------------------------------------------------------------------
+// i < NLO is known at compile time to be a real frame; only the NB-NLO tail
+template <int K>
+__device__ __forceinline__ float tree_sum(const float (&v)[K]) {
+    float t[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) t[k] = v[k];
+#pragma unroll
+    for (int w = K / 2; w >= 1; w /= 2) {
+#pragma unroll
+        for (int k = 0; k < w; ++k) t[k] = t[2 * k] + t[2 * k + 1];
+    }
+    return t[0];
+}
+
+// Sweep design (see DESIGN.md "meanclip"): the samples stay in registers as
+// y = x - pivot, two per 64-bit register pair so that the Blackwell packed
+// FADD2 / FFMA2 instructions update two samples per issue slot.  A rejected
+// sample is overwritten with 0 (it then adds nothing to the running sums).  A
+// sweep walks the samples in groups of 8: the common path per group is 4 FADD2
+// (t = y - c), 4 FADD2 + 4 FFMA2 (sums), the |t| maximum, one compare -- no
+// per-sample predicates or selects.  Only a group whose largest |y - c| reaches
+// the inner clip bound is revisited, sample by sample, in a second "rare" pass.
+constexpr int meanclip_min_blocks(int NB) {
+    return NB <= 32 ? 6 : (NB <= 48 ? 5 : (NB <= 100 ? 4 : (NB <= 128 ? 3 : 2)));
+}
+
+// The per-pixel work, given the N raw samples of pixel p in y[] (padding = 0).
+template <int NB, int NLO, bool SYM>
+__device__ __forceinline__ void meanclip_pixel(float2 (&y)[NB / 2], const FramePtrs<NB>& fp,
+                                               const StackArgs& a, const int64_t p) {
+    static_assert(NB % 2 == 0, "meanclip buckets must be even");
+    const int N = a.N;
+    constexpr int NP = NB / 2;                         // register pairs
+    constexpr int GP = 4;                              // pairs (8 samples) per group
+    constexpr int NG = (NP + GP - 1) / GP;
+    static_assert(NG <= 64, "flag word too small");
+
+    // Pivot: median of the first three frames (robust to one outlier).  All
+    // float32 arithmetic below is on y = x - pivot: sums stay small and the
+    // variance is free of catastrophic cancellation.
+    const float pivot = med3(y[0].x, y[0].y, y[1].x);
+    const float2 negpiv = make_float2(-pivot, -pivot);
+    float S1 = 0.f, S2 = 0.f;
+#pragma unroll
+    for (int gidx = 0; gidx < NG; ++gidx) {
+        float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < GP; ++k) {
+            const int j = gidx * GP + k;
+            if (j < NP) {
+                float2 d = __fadd2_rn(y[j], negpiv);
+                if (2 * j >= NLO)                          // bucket tail: padding beyond N becomes y = 0
+                    d = __fmul2_rn(d, make_float2(a.tailmask[2 * j - NLO], a.tailmask[2 * j + 1 - NLO]));
+                y[j] = d;
+                s1 = __fadd2_rn(s1, d);
+                s2 = __ffma2_rn(d, d, s2);
+            }
+        }
+        S1 += s1.x + s1.y;
+        S2 += s2.x + s2.y;
+    }
+    // NaN input poisons S1/S2, inf input (or overflow) makes S2 infinite: the
+    // generic routine owns those semantics.
+    if (!(S2 <= FLT_MAX) || !(fabsf(S1) <= FLT_MAX)) { generic_pixel<NB>(fp, a, p); return; }
+
+    int nk = N;
+    const float klo = (float)a.klo, khi = (float)a.khi;
+    const float kmax = fmaxf(klo, khi);
+    bool uncertain = false;
+    int it = 0;
+    while (a.maxiters != 0 && (a.maxiters < 0 || it < a.maxiters)) {
+        ++it;
+        if (S2 == 0.f) break;            // all survivors equal the pivot: bounds [c,c], nothing to reject
+        const float fn = (float)nk;
+        const float c = S1 / fn;
+        const float ex2 = S2 / fn;
+        const float var = ex2 - c * c;
+        const float sd = sqrtf(fmaxf(var, 0.f));
+        // Bound on |threshold_f32 - threshold_exact| + |y_f32 - y_exact|:
+        // group-wise summation (GP + 1 + NG terms deep), unit roundoff doubled for safety.
+        const float u2 = 1.1920929e-7f;                       // 2^-23
+        const float m = (float)(GP + NG + 9);
+        const float g = m * u2 * (sqrtf(ex2) + 1.5f * kmax * ex2 / sd) + 6.f * u2 * (fabsf(c) + kmax * sd);
+        if (!(g < 0.25f * kmax * sd)) { uncertain = true; break; }   // degenerate (var ~ 0): let float64 decide
+        // inner (certainly kept inside) and outer (certainly rejected outside) bounds on t = y - c
+        const float lo_in = -klo * sd + g, lo_out = -klo * sd - g;
+        const float hi_in = khi * sd - g, hi_out = khi * sd + g;
+        const float t_in = fminf(-lo_in, hi_in);              // symmetric inner bound on |t|
+        const float ylo_out = c + lo_out, ylo_in = c + lo_in, yhi_in = c + hi_in, yhi_out = c + hi_out;
+        // A rejected sample is overwritten with y = 0 (the pivot), so the pivot itself must sit
+        // strictly inside the inner bounds: then zeros are never rejected (again) and add nothing.
+        if (!(ylo_in < 0.f && yhi_in > 0.f)) { uncertain = true; break; }
+        const float2 negc = make_float2(-c, -c);
+        const int nk_before = nk;
+        uint64_t flags = 0;              // bit g: group g holds a sample outside the inner bounds
+        // test pass: tight straight-line code, no per-sample predicates, no sums (the sums of
+        // the survivors only change when something is rejected)
+#pragma unroll
+        for (int gidx = 0; gidx < NG; ++gidx) {
+            float tmax = 0.f, tmin = 0.f;
+#pragma unroll
+            for (int k = 0; k < GP; ++k) {
+                const int j = gidx * GP + k;
+                if (j < NP) {
+                    const float2 t = __fadd2_rn(y[j], negc);
+                    if (SYM) {
+                        tmax = fmaxf(tmax, fmaxf(fabsf(t.x), fabsf(t.y)));
+                    } else {
+                        tmax = fmaxf(tmax, fmaxf(t.x, t.y));
+                        tmin = fminf(tmin, fminf(t.x, t.y));
+                    }
+                }
+            }
+            const bool flagged = SYM ? (tmax >= t_in) : (tmax >= hi_in || tmin <= lo_in);
+            if (flagged) flags |= (uint64_t)1 << gidx;
+        }
+        if (flags == 0) break;           // every survivor is certainly inside the bounds: converged
+        // update pass: flagged groups sample by sample, the others with packed sums
+        float n1 = 0.f, n2 = 0.f;
+#pragma unroll
+        for (int gidx = 0; gidx < NG; ++gidx) {
+            if ((flags >> gidx) & 1) {
+                float g1 = 0.f, g2 = 0.f, vmax = 0.f, vmin = 0.f;
+#pragma unroll
+                for (int k = 0; k < 2 * GP; ++k) {
+                    const int i = gidx * 2 * GP + k;
+                    if (i < NB) {
+                        // compare y against bounds shifted by c (not t = y - c: keeps the
+                        // compiler from holding every t of the test pass live in registers)
+                        float v = (i & 1) ? y[i >> 1].y : y[i >> 1].x;
+                        const bool keep = (v >= ylo_out) && (v <= yhi_out);
+                        nk -= keep ? 0 : 1;                      // certainly rejected
+                        v = keep ? v : 0.f;
+                        if (i & 1) y[i >> 1].y = v; else y[i >> 1].x = v;
+                        vmax = fmaxf(vmax, v);
+                        vmin = fminf(vmin, v);
+                        g1 += v;
+                        g2 = fmaf(v, v, g2);
+                    }
+                }
+                // a survivor inside the guard band: float64 must decide
+                if (!(vmin > ylo_in && vmax < yhi_in)) uncertain = true;
+                n1 += g1;
+                n2 += g2;
+            } else {
+                float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < GP; ++k) {
+                    const int j = gidx * GP + k;
+                    if (j < NP) {
+                        s1 = __fadd2_rn(s1, y[j]);
+                        s2 = __ffma2_rn(y[j], y[j], s2);
+                    }
+                }
+                n1 += s1.x + s1.y;
+                n2 += s2.x + s2.y;
+            }
+        }
+        if (uncertain) break;
+        S1 = n1;
+        S2 = n2;
+        if (nk == nk_before || nk == 0) break;
+    }
+    if (uncertain || nk == 0) { generic_pixel<NB>(fp, a, p); return; }
+
+    // mean of the survivors = pivot + sum(y)/nk (rejected samples are zeros).
+    // float32 output: the float32 sums of the small shifted values are accurate
+    // to ~1e-8 of max(|mean|, sigma).  float64 output: the shifted values are
+    // summed in float64 (exact), leaving only the rounding of y = x - pivot
+    // itself (none when x and pivot are within a factor 2, Sterbenz).
+    double sum1 = (double)S1, sum2 = (double)S2;
+    if (a.out_f64) {
+        sum1 = 0.0; sum2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            const double d0 = (double)y[j].x, d1 = (double)y[j].y;
+            sum1 = __dadd_rn(__dadd_rn(sum1, d0), d1);
+            sum2 = __dadd_rn(__dadd_rn(sum2, __dmul_rn(d0, d0)), __dmul_rn(d1, d1));
+        }
+    }
+    const double cy = __ddiv_rn(sum1, (double)nk);
+    const double mean = __dadd_rn((double)pivot, cy);
+    double unc_out = (double)NAN;
+    if (a.uncert) {
+        double var = __dsub_rn(__ddiv_rn(sum2, (double)nk), __dmul_rn(cy, cy));
+        unc_out = __ddiv_rn(__dsqrt_rn(var > 0.0 ? var : 0.0), __dsqrt_rn((double)nk));
+    }
+    write_pixel(a, p, mean, N - nk, unc_out, 0);
+}
+
+// Direct kernel: one block per 128-pixel tile, samples loaded straight from
+// global memory.
+template <int NB, int NLO, bool SYM>
+__global__ void __launch_bounds__(TPB, meanclip_min_blocks(NB))
+stack_meanclip_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_constant__ StackArgs a) {
+    const int64_t p = a.pix0 + (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (p >= a.pix0 + a.npix) return;
+    const uint32_t p32 = (uint32_t)p;                  // host guarantees H*W < 2^32
+    float2 y[NB / 2];
+#pragma unroll
+    for (int j = 0; j < NB / 2; ++j) {                 // padding slots point at frame 0 (masked later)
+        y[j].x = ld_stream(fp.p[2 * j] + p32);
+        y[j].y = ld_stream(fp.p[2 * j + 1] + p32);
+    }
+    meanclip_pixel<NB, NLO, SYM>(y, fp, a, p);
+}
+
+// ---------------------------------------------------------------------------
+// TMA-staged persistent kernel (opt-in: APGPU_STACK_USE_TMA)
+// ---------------------------------------------------------------------------
+// meanclip_min_blocks(NB)/2 persistent 256-thread CTAs per SM walk the 256-pixel
+// tiles of the band.  For each tile one warp issues N bulk asynchronous copies
+// (cp.async.bulk global -> shared, 1 KB contiguous of each frame, completion
+// counted on an mbarrier); the threads pull their column out of shared memory
+// into registers (conflict-free LDS), release the stage with one __syncthreads,
+// and the copies for the CTA's NEXT tile are issued before the arithmetic on the
+// current one starts.  Measured on B200 (profiles/): correct, but 20 % SLOWER
+// than the direct kernel at N=100 -- the per-tile CTA barrier makes every warp
+// wait for the CTA's slowest pixel (clip iteration counts differ per pixel) --
+// so the dispatcher only uses it on request.
+// moves 1 KB (512-byte copies are TMA-issue bound).
+constexpr int TTPB = 256;
+
+template <int NB>
+__device__ __forceinline__ void issue_tile_copies(const FramePtrs<NB>& fp, int N, int64_t pix, float* stage,
+                                                  uint64_t* bar) {
+    // called by warp 0
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) mbar_expect_tx(bar, (uint32_t)N * TTPB * sizeof(float));
+    __syncwarp();
+    for (int i = lane; i < N; i += 32)
+        bulk_copy_g2s(stage + i * TTPB, fp.p[i] + pix, TTPB * sizeof(float), bar);
+}
+
+template <int NB, int NLO, bool SYM>
+__global__ void __launch_bounds__(TTPB, meanclip_min_blocks(NB) / 2)
+stack_meanclip_tma_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_constant__ StackArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* stage = reinterpret_cast<float*>(smem_raw);                       // [NB][TTPB]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NB * TTPB * sizeof(float));
+    const int N = a.N;
+    const int64_t ntiles = a.npix / TTPB;                                    // full tiles only (host launches the tail)
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    for (int i = N * TTPB + threadIdx.x; i < NB * TTPB; i += TTPB) stage[i] = 0.f;   // padding rows: never copied into
+    __syncthreads();
+    int64_t tile = blockIdx.x;
+    uint32_t parity = 0;
+    if (tile < ntiles && threadIdx.x < 32) issue_tile_copies<NB>(fp, N, a.pix0 + tile * TTPB, stage, bar);
+    for (; tile < ntiles; tile += gridDim.x) {
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+        float2 y[NB / 2];
+#pragma unroll
+        for (int j = 0; j < NB / 2; ++j) {
+            y[j].x = stage[(2 * j) * TTPB + threadIdx.x];
+            y[j].y = stage[(2 * j + 1) * TTPB + threadIdx.x];
+        }
+        __syncthreads();                                                     // every thread has drained the stage
+        const int64_t next = tile + gridDim.x;
+        if (next < ntiles && threadIdx.x < 32) issue_tile_copies<NB>(fp, N, a.pix0 + next * TTPB, stage, bar);
+        meanclip_pixel<NB, NLO, SYM>(y, fp, a, a.pix0 + tile * TTPB + threadIdx.x);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// cp.async-staged persistent kernel: warp-granular software pipeline
+// ---------------------------------------------------------------------------
+// Every warp is its own pipeline: it owns a private [N][32-pixel] shared-memory
+// stage, fills it with 16-byte asynchronous copies (cp.async / LDGSTS: one warp
+// instruction moves the 128-byte rows of four frames), drains it into registers,
+// immediately re-arms it with the copies for its NEXT tile and only then does
+// the arithmetic.  No CTA barrier anywhere, so a warp never waits for another
+// warp's slow pixel (the flaw of the CTA-wide TMA variant above), the HBM latency
+// of tile t+1 hides behind the compute of tile t without extra registers, and
+// the instruction stream has 1/4 of the load instructions and no per-sample
+// 64-bit address arithmetic.
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+constexpr int WT = 32;      // pixels per warp tile
+
+__device__ __forceinline__ void issue_warp_tile(const float* const* ptab, int N, int64_t pix, float* stage, int lane) {
+    const int sub = lane >> 3;            // which of the 4 frames of this instruction
+    const int off = (lane & 7) * 4;       // 4 pixels (16 bytes) per lane
+    for (int i0 = 0; i0 < N; i0 += 4) {
+        const int i = i0 + sub;
+        if (i < N) cp_async16(stage + i * WT + off, ptab[i] + pix + off);
+    }
+    cp_async_commit();
+}
+
+template <int NB, int NLO, bool SYM>
+__global__ void __launch_bounds__(TPB, meanclip_min_blocks(NB))
+stack_meanclip_cpasync_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_constant__ StackArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const float** ptab = reinterpret_cast<const float**>(smem_raw);           // [NB] frame pointers
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* stage = reinterpret_cast<float*>(smem_raw + (size_t)NB * sizeof(float*)) + (size_t)warp * NB * WT;
+    const int N = a.N;
+    for (int i = threadIdx.x; i < N; i += TPB) ptab[i] = fp.p[i];
+    for (int i = N * WT + lane; i < NB * WT; i += 32) stage[i] = 0.f;         // padding rows: never copied into
+    __syncthreads();
+    const int64_t ntiles = a.npix / WT;                                       // full warp tiles (host launches the tail)
+    const int64_t nwarps = (int64_t)gridDim.x * (TPB / 32);
+    int64_t tile = (int64_t)blockIdx.x * (TPB / 32) + warp;
+    if (tile < ntiles) issue_warp_tile(ptab, N, a.pix0 + tile * WT, stage, lane);
+    for (; tile < ntiles; tile += nwarps) {
+        cp_async_wait_all();
+        __syncwarp();                                                         // every lane's copies are visible
+        float2 y[NB / 2];
+#pragma unroll
+        for (int j = 0; j < NB / 2; ++j) {
+            y[j].x = stage[(2 * j) * WT + lane];
+            y[j].y = stage[(2 * j + 1) * WT + lane];
+        }
+        __syncwarp();                                                         // stage drained by every lane
+        const int64_t next = tile + nwarps;
+        if (next < ntiles) issue_warp_tile(ptab, N, a.pix0 + next * WT, stage, lane);
+        meanclip_pixel<NB, NLO, SYM>(y, fp, a, a.pix0 + tile * WT + lane);
+    }
+}
+
+template <int NB, int NLO, bool SYM>
+int launch_meanclip_sym(const FramePtrs<NB>& fp, const StackArgs& a, int staging, cudaStream_t st) {
+    // staging: 0 direct global loads, 1 CTA-wide TMA bulk copies, 2 warp-granular cp.async pipeline
+    StackArgs rest = a;
+    if (staging == 2) {
+        const int64_t ntiles = a.npix / WT;
+        if (ntiles > 0) {
+            const size_t smem = (size_t)NB * sizeof(float*) + (size_t)(TPB / 32) * NB * WT * sizeof(float);
+            APGPU_CUDA(cudaFuncSetAttribute(stack_meanclip_cpasync_kernel<NB, NLO, SYM>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int64_t grid = (int64_t)APGPU_NUM_SMS * meanclip_min_blocks(NB);
+            const int64_t need = (ntiles + TPB / 32 - 1) / (TPB / 32);
+            if (grid > need) grid = need;
+            stack_meanclip_cpasync_kernel<NB, NLO, SYM><<<(unsigned)grid, TPB, smem, st>>>(fp, a);
+            APGPU_LAUNCH_CHECK("stack_meanclip_cpasync_kernel");
+        }
+        rest.pix0 = a.pix0 + ntiles * WT;            // the < 32-pixel tail goes through the direct kernel
+        rest.npix = a.npix - ntiles * WT;
+    }
+    if constexpr (meanclip_min_blocks(NB) % 2 == 0) {
+        if (staging == 1) {
+            const int64_t ntiles = a.npix / TTPB;
+            if (ntiles > 0) {
+                const size_t smem = (size_t)NB * TTPB * sizeof(float) + 16;
+                APGPU_CUDA(cudaFuncSetAttribute(stack_meanclip_tma_kernel<NB, NLO, SYM>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                int64_t grid = (int64_t)APGPU_NUM_SMS * (meanclip_min_blocks(NB) / 2);
+                if (grid > ntiles) grid = ntiles;
+                stack_meanclip_tma_kernel<NB, NLO, SYM><<<(unsigned)grid, TTPB, smem, st>>>(fp, a);
+                APGPU_LAUNCH_CHECK("stack_meanclip_tma_kernel");
+            }
+            rest.pix0 = a.pix0 + ntiles * TTPB;      // the < 256-pixel tail goes through the direct kernel
+            rest.npix = a.npix - ntiles * TTPB;
+        }
+    }
+    if (rest.npix > 0) {
+        int64_t blocks = (rest.npix + TPB - 1) / TPB;
+        stack_meanclip_kernel<NB, NLO, SYM><<<(unsigned)blocks, TPB, 0, st>>>(fp, rest);
+        APGPU_LAUNCH_CHECK("stack_meanclip_kernel");
+    }
+    return APGPU_OK;
+}
+
+template <int NB, int NLO>
+int launch_meanclip(const float* const* frames, const StackArgs& a_in, cudaStream_t st, int flags) {
+    static_assert(NB - NLO <= MEANCLIP_MAX_TAIL, "tail mask too small");
+    FramePtrs<NB> fp;
+    for (int i = 0; i < NB; ++i) fp.p[i] = i < a_in.N ? frames[i] : frames[0];   // padding: loaded, then masked
+    StackArgs a = a_in;
+    for (int i = NLO; i < NB; ++i) a.tailmask[i - NLO] = i < a.N ? 1.f : 0.f;
+    // asynchronous copies need 16-byte aligned sources: frame base + first pixel of the band
+    // default (measured, bench.py variants): the warp-granular cp.async pipeline wins for the
+    // shorter stacks (N=30: +8 %), direct loads are level or slightly ahead from N~80 up
+    int staging = (flags & APGPU_STACK_USE_TMA) ? 1 : ((flags & APGPU_STACK_DIRECT_LOADS) ? 0 : (NB <= 64 ? 2 : 0));
+    if (flags & APGPU_STACK_USE_CPASYNC) staging = 2;
+    // the per-warp stages must leave room for meanclip_min_blocks CTAs per SM
+    const size_t smem_cta = (size_t)NB * sizeof(float*) + (size_t)(TPB / 32) * NB * WT * sizeof(float);
+    if (staging == 2 && smem_cta * meanclip_min_blocks(NB) > (size_t)SMEM_MAX_BYTES) staging = 0;
+    for (int i = 0; i < a.N; ++i)
+        if (!apgpu_aligned(frames[i] + a.pix0, 16)) staging = 0;
+    if ((float)a.klo == (float)a.khi) return launch_meanclip_sym<NB, NLO, true>(fp, a, staging, st);
+    return launch_meanclip_sym<NB, NLO, false>(fp, a, staging, st);
+}
+
+#define MC_CASE(NB_, NLO_) if (nb == NB_) return launch_meanclip<NB_, NLO_>(frames, a, st, flags);
+
+}  // namespace apgpu_stack

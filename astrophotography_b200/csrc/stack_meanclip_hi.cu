@@ -1,0 +1,11 @@
+// meanclip<NB, NLO> instantiations, part "hi" (split so that nvcc compiles the buckets in parallel)
+#include "stack_meanclip.cuh"
+
+namespace apgpu_stack {
+
+int stack_dispatch_meanclip_hi(int nb, const float* const* frames, const StackArgs& a, cudaStream_t st, int flags) {
+    MC_CASE(160, 128) MC_CASE(200, 160)
+    return APGPU_ERR_UNSUPPORTED;
+}
+
+}  // namespace apgpu_stack

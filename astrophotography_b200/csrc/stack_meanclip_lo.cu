@@ -1,0 +1,11 @@
+// meanclip<NB, NLO> instantiations, part "lo" (split so that nvcc compiles the buckets in parallel)
+#include "stack_meanclip.cuh"
+
+namespace apgpu_stack {
+
+int stack_dispatch_meanclip_lo(int nb, const float* const* frames, const StackArgs& a, cudaStream_t st, int flags) {
+    MC_CASE(8, 2) MC_CASE(16, 8) MC_CASE(24, 16) MC_CASE(32, 24) MC_CASE(48, 32) MC_CASE(64, 48)
+    return APGPU_ERR_UNSUPPORTED;
+}
+
+}  // namespace apgpu_stack

@@ -1,0 +1,169 @@
+// Frame-stack reducer: sorted<NB, NLO, MODE> register-resident Batcher-network kernels.  See stack_common.cuh.
+#pragma once
+#include "stack_common.cuh"
+#include "sort_networks.inc"
+
+namespace apgpu_stack {
+
+// ---------------------------------------------------------------------------
+// sorted<NB, NLO, MODE>: Batcher network in registers, N in (NLO, NB]
+// ---------------------------------------------------------------------------
+constexpr int STPB = 256;         // threads per CTA of the sorted kernels (lock-stepped, see sort_regs)
+constexpr int MODE_MED = 0;       // method=median, no clipping
+constexpr int MODE_MEDMAD1 = 1;   // one median/MAD clip pass, then the mean (ApMasterCal)
+
+#define CE_X(i, j) { float lo_ = fminf(x[i], x[j]); float hi_ = fmaxf(x[i], x[j]); x[i] = lo_; x[j] = hi_; }
+
+// Every 128 comparators the network has a CTA barrier: the 8 warps of a CTA walk the ~35 KB of
+// straight-line code together, so one instruction-cache fill serves all of them (ncu before:
+// `no_instruction` was the top stall of the median/MAD kernel).  The network is branch-free
+// and data-independent, so the barrier costs no load imbalance.
+#define SY_X() __syncthreads();
+template <int NB> __device__ __forceinline__ void sort_regs(float (&x)[NB]);
+#define APGPU_DEF_SORT(n) \
+    template <> __device__ __forceinline__ void sort_regs<n>(float (&x)[n]) { APGPU_SORTNET_##n(CE_X, SY_X) }
+APGPU_DEF_SORT(4) APGPU_DEF_SORT(8) APGPU_DEF_SORT(12) APGPU_DEF_SORT(16) APGPU_DEF_SORT(20)
+APGPU_DEF_SORT(24) APGPU_DEF_SORT(32) APGPU_DEF_SORT(40) APGPU_DEF_SORT(48) APGPU_DEF_SORT(56)
+APGPU_DEF_SORT(64) APGPU_DEF_SORT(72) APGPU_DEF_SORT(80) APGPU_DEF_SORT(90) APGPU_DEF_SORT(100)
+APGPU_DEF_SORT(112) APGPU_DEF_SORT(128)
+
+template <int NB, int NLO, int MODE>
+__global__ void __launch_bounds__(STPB, (NB <= 32 ? 4 : (NB <= 100 ? 2 : 1)))
+stack_sorted_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_constant__ StackArgs a) {
+    extern __shared__ float col[];       // MODE_MEDMAD1: [NB + 2][TPB] sorted columns + guard rows
+    // no early exit: the sort contains CTA barriers.  Threads past the end redo the last pixel
+    // and skip the write.
+    const int64_t pend = a.pix0 + a.npix;
+    int64_t p = a.pix0 + (int64_t)blockIdx.x * STPB + threadIdx.x;
+    const bool valid = p < pend;
+    if (!valid) p = pend - 1;
+    const int N = a.N;
+    // Pad to NB with -inf / +inf split so that the real samples sit centred in
+    // the sorted array: the median is then at the compile-time index NB/2-1
+    // (and NB/2 for even N) whatever N is.
+    const int npad = NB - N;
+    const int nneg = npad >> 1;          // -inf pads; the other npad-nneg are +inf
+    const uint32_t p32 = (uint32_t)p;    // host guarantees H*W < 2^32: one IMAD.WIDE per address
+    float x[NB];
+    float z = 0.f;
+    double sum_all = 0.0;
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        if (APGPU_ACTIVE(i)) {
+            x[i] = ld_stream(fp.p[i] + p32);
+        } else {
+            x[i] = (i - N < nneg) ? -INFINITY : INFINITY;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        if (APGPU_ACTIVE(i)) {
+            z = fmaf(x[i], 0.f, z);
+            if (MODE == MODE_MEDMAD1) sum_all = __dadd_rn(sum_all, (double)x[i]);   // frame order, as nanmean
+        }
+    }
+    const bool nonfinite = (z != z);          // handled after the (barrier-carrying) sort
+
+    sort_regs<NB>(x);
+    if (!valid) return;
+    if (nonfinite) { generic_pixel<NB>(fp, a, p); return; }
+
+    constexpr int C = NB / 2;
+    const double med = (N & 1) ? (double)x[C - 1]
+                               : __dmul_rn(__dadd_rn((double)x[C - 1], (double)x[C]), 0.5);
+    if (MODE == MODE_MED) {
+        write_pixel(a, p, med, 0, (double)NAN, 0);
+        return;
+    }
+
+    // Park the sorted column in shared memory ([row][thread]: conflict-free for
+    // any per-thread row index) for the data-dependent selection below.  Row 0
+    // and row NB+1 are -inf / +inf guards, so together with the +-inf padding
+    // every row outside the real samples has an infinite deviation from the
+    // median and the merge below needs no bounds checks.
+    float* s = col + threadIdx.x + STPB;          // s[i * STPB] = sorted sample i, i in [-1, NB]
+    s[-STPB] = -INFINITY;
+    s[NB * STPB] = INFINITY;
+#pragma unroll
+    for (int i = 0; i < NB; ++i) s[i * STPB] = x[i];
+    const int base = nneg;               // real samples occupy rows [base, base + N)
+    // MAD = median of |x - med|.  Left of the median the deviations grow towards row
+    // `base`, right of it towards row `base+N`: two sorted lists,
+    //     L[j] = med - s[l0 - j]   (j = 0 .. nL-1),   R[j] = s[l0 + 1 + j] - med   (j = 0 .. nR-1),
+    // whose (k+1)-th smallest element is found by bisecting on how many come from L
+    // (O(log N) shared-memory reads, float64, exact).  Guard rows / +-inf padding give
+    // every out-of-range index an infinite deviation.
+    const int l0 = base + ((N - 1) >> 1);
+    const int nL = l0 - base + 1, nR = N - nL;
+    auto devL = [&](int j) { return fabs(__dsub_rn((double)s[(l0 - j) * STPB], med)); };
+    auto devR = [&](int j) { return fabs(__dsub_rn((double)s[(l0 + 1 + j) * STPB], med)); };
+    const int k1 = (N - 1) >> 1;                       // 0-based rank of the lower middle deviation
+    int lo_i = k1 + 1 - nR > 0 ? k1 + 1 - nR : 0;
+    int hi_i = k1 + 1 < nL ? k1 + 1 : nL;
+    while (lo_i < hi_i) {
+        const int mid = (lo_i + hi_i) >> 1;
+        if (devL(mid) < devR(k1 - mid)) lo_i = mid + 1; else hi_i = mid;
+    }
+    // lo_i samples of the k1+1 smallest deviations come from L, k1+1-lo_i from R
+    const double la = lo_i > 0 ? devL(lo_i - 1) : -1.0;
+    const double ra = (k1 - lo_i) >= 0 ? devR(k1 - lo_i) : -1.0;
+    const double d1 = la > ra ? la : ra;
+    const double lb = devL(lo_i), rb = devR(k1 + 1 - lo_i);      // the next deviation up (inf past the ends)
+    const double d2 = lb < rb ? lb : rb;
+    const double mad = (N & 1) ? d1 : __dmul_rn(__dadd_rn(d1, d2), 0.5);
+    const double sd = __dmul_rn(MAD_TO_STD, mad);
+    const double lo = __dsub_rn(med, __dmul_rn(sd, a.klo));
+    const double hi = __dadd_rn(med, __dmul_rn(sd, a.khi));
+    int sa = base, sb = base + N;
+    while (sa < sb && (double)s[sa * STPB] < lo) ++sa;
+    while (sa < sb && (double)s[(sb - 1) * STPB] > hi) --sb;
+    const int nk = sb - sa;
+#ifdef APGPU_DEBUG_MEDMAD
+    if (p == a.pix0) printf("dbg N=%d NB=%d base=%d med=%.6f d1=%.6f d2=%.6f mad=%.6f lo=%.6f hi=%.6f sa=%d sb=%d klo=%f\n",
+        N, NB, base, med, d1, d2, mad, lo, hi, sa, sb, a.klo);
+#endif
+    double mean;
+    if (nk == N) {
+        mean = __ddiv_rn(sum_all, (double)N);
+    } else {
+        double acc = 0.0;
+        for (int i = sa; i < sb; ++i) acc = __dadd_rn(acc, (double)s[i * STPB]);
+        mean = __ddiv_rn(acc, (double)nk);      // nk >= 1: the median itself always survives
+    }
+    double unc = (double)NAN;
+    if (a.uncert) {
+        double acc = 0.0;
+        for (int i = sa; i < sb; ++i) {
+            double d = __dsub_rn((double)s[i * STPB], mean);
+            acc = __dadd_rn(acc, __dmul_rn(d, d));
+        }
+        unc = __ddiv_rn(__dsqrt_rn(__ddiv_rn(acc, (double)nk)), __dsqrt_rn((double)nk));
+    }
+    write_pixel(a, p, mean, N - nk, unc, 0);
+}
+
+template <int NB, int NLO, int MODE>
+int launch_sorted(const float* const* frames, const StackArgs& a, cudaStream_t st) {
+    FramePtrs<NB> fp;
+    for (int i = 0; i < NB; ++i) fp.p[i] = i < a.N ? frames[i] : nullptr;
+    int64_t blocks = (a.npix + STPB - 1) / STPB;
+    size_t smem = (MODE == MODE_MEDMAD1) ? (size_t)(NB + 2) * STPB * sizeof(float) : 0;
+    if (smem > 48 * 1024)
+        APGPU_CUDA(cudaFuncSetAttribute(stack_sorted_kernel<NB, NLO, MODE>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    stack_sorted_kernel<NB, NLO, MODE><<<(unsigned)blocks, STPB, smem, st>>>(fp, a);
+    APGPU_LAUNCH_CHECK("stack_sorted_kernel");
+    return APGPU_OK;
+}
+
+#define SO_CASE(NB_, NLO_) if (nb == NB_) return launch_sorted<NB_, NLO_, MODE>(frames, a, st);
+
+template <int MODE>
+int dispatch_sorted(int nb, const float* const* frames, const StackArgs& a, cudaStream_t st) {
+    SO_CASE(4, 0) SO_CASE(8, 4) SO_CASE(12, 8) SO_CASE(16, 12) SO_CASE(20, 16) SO_CASE(24, 20)
+    SO_CASE(32, 24) SO_CASE(40, 32) SO_CASE(48, 40) SO_CASE(56, 48) SO_CASE(64, 56) SO_CASE(72, 64)
+    SO_CASE(80, 72) SO_CASE(90, 80) SO_CASE(100, 90) SO_CASE(112, 100) SO_CASE(128, 112)
+    return APGPU_ERR_UNSUPPORTED;
+}
+
+}  // namespace apgpu_stack
