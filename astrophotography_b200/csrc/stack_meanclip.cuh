@@ -77,6 +77,17 @@ __device__ __forceinline__ void meanclip_pixel(float2 (&y)[NB / 2], const FrameP
     const float kmax = fmaxf(klo, khi);
     bool uncertain = false;
     int it = 0;
+    // Sums after a rejection are updated by SUBTRACTING the rejected samples' contributions
+    // while that is accurate (what is left of sum(y^2) is at least half of the last fully
+    // summed value S2_fresh: the rounding errors, bounded relative to the old sums, are then at
+    // most doubled relative to the new ones -- m below grows accordingly); a pixel that loses
+    // more than that (a cosmic-ray hit) has its sums rebuilt from the registers.
+    float S2_fresh = S2;
+    int nsub = 0;
+    // M_prev: an upper bound on |y - c_prev| over the survivors of the previous iteration.  When
+    // M_prev + |c - c_prev| is below the new inner bound, every survivor is certainly inside
+    // the new clip limits: converged without another pass over the samples.
+    float M_prev = -1.f, c_prev = 0.f;
     while (a.maxiters != 0 && (a.maxiters < 0 || it < a.maxiters)) {
         ++it;
         if (S2 == 0.f) break;            // all survivors equal the pivot: bounds [c,c], nothing to reject
@@ -86,9 +97,11 @@ __device__ __forceinline__ void meanclip_pixel(float2 (&y)[NB / 2], const FrameP
         const float var = ex2 - c * c;
         const float sd = sqrtf(fmaxf(var, 0.f));
         // Bound on |threshold_f32 - threshold_exact| + |y_f32 - y_exact|:
-        // group-wise summation (GP + 1 + NG terms deep), unit roundoff doubled for safety.
+        // group-wise summation (GP + 1 + NG terms deep), unit roundoff doubled for safety;
+        // after nsub subtractive updates the summation error is relative to sums up to twice
+        // as large, plus one rounding per subtraction.
         const float u2 = 1.1920929e-7f;                       // 2^-23
-        const float m = (float)(GP + NG + 9);
+        const float m = (float)(GP + NG + 9) + (nsub ? (float)(GP + NG + 9 + 2 * nsub) : 0.f);
         const float g = m * u2 * (sqrtf(ex2) + 1.5f * kmax * ex2 / sd) + 6.f * u2 * (fabsf(c) + kmax * sd);
         if (!(g < 0.25f * kmax * sd)) { uncertain = true; break; }   // degenerate (var ~ 0): let float64 decide
         // inner (certainly kept inside) and outer (certainly rejected outside) bounds on t = y - c
@@ -99,9 +112,10 @@ __device__ __forceinline__ void meanclip_pixel(float2 (&y)[NB / 2], const FrameP
         // A rejected sample is overwritten with y = 0 (the pivot), so the pivot itself must sit
         // strictly inside the inner bounds: then zeros are never rejected (again) and add nothing.
         if (!(ylo_in < 0.f && yhi_in > 0.f)) { uncertain = true; break; }
+        if (M_prev >= 0.f && (M_prev + fabsf(c - c_prev)) * 1.000002f < t_in) break;   // converged, no pass needed
         const float2 negc = make_float2(-c, -c);
-        const int nk_before = nk;
         uint64_t flags = 0;              // bit g: group g holds a sample outside the inner bounds
+        float M_nf = 0.f;                // max |y - c| over the groups that are not flagged
         // test pass: tight straight-line code, no per-sample predicates, no sums (the sums of
         // the survivors only change when something is rejected)
 #pragma unroll
@@ -122,36 +136,51 @@ __device__ __forceinline__ void meanclip_pixel(float2 (&y)[NB / 2], const FrameP
             }
             const bool flagged = SYM ? (tmax >= t_in) : (tmax >= hi_in || tmin <= lo_in);
             if (flagged) flags |= (uint64_t)1 << gidx;
+            const float tabs = SYM ? tmax : fmaxf(tmax, -tmin);
+            M_nf = fmaxf(M_nf, flagged ? 0.f : tabs);
         }
         if (flags == 0) break;           // every survivor is certainly inside the bounds: converged
-        // update pass: flagged groups sample by sample, the others with packed sums
-        float n1 = 0.f, n2 = 0.f;
+        // rejection pass over the flagged groups, sample by sample
+        float r1 = 0.f, r2 = 0.f;        // sums over the samples rejected in this iteration
+        float vmax = 0.f, vmin = 0.f;    // range of the survivors (and zeros) of the flagged groups
 #pragma unroll
         for (int gidx = 0; gidx < NG; ++gidx) {
             if ((flags >> gidx) & 1) {
-                float g1 = 0.f, g2 = 0.f, vmax = 0.f, vmin = 0.f;
 #pragma unroll
                 for (int k = 0; k < 2 * GP; ++k) {
                     const int i = gidx * 2 * GP + k;
                     if (i < NB) {
                         // compare y against bounds shifted by c (not t = y - c: keeps the
                         // compiler from holding every t of the test pass live in registers)
-                        float v = (i & 1) ? y[i >> 1].y : y[i >> 1].x;
+                        const float v = (i & 1) ? y[i >> 1].y : y[i >> 1].x;
                         const bool keep = (v >= ylo_out) && (v <= yhi_out);
                         nk -= keep ? 0 : 1;                      // certainly rejected
-                        v = keep ? v : 0.f;
-                        if (i & 1) y[i >> 1].y = v; else y[i >> 1].x = v;
-                        vmax = fmaxf(vmax, v);
-                        vmin = fminf(vmin, v);
-                        g1 += v;
-                        g2 = fmaf(v, v, g2);
+                        const float vr = keep ? 0.f : v;
+                        const float vk = keep ? v : 0.f;
+                        if (i & 1) y[i >> 1].y = vk; else y[i >> 1].x = vk;
+                        vmax = fmaxf(vmax, vk);
+                        vmin = fminf(vmin, vk);
+                        r1 += vr;
+                        r2 = fmaf(vr, vr, r2);
                     }
                 }
-                // a survivor inside the guard band: float64 must decide
-                if (!(vmin > ylo_in && vmax < yhi_in)) uncertain = true;
-                n1 += g1;
-                n2 += g2;
-            } else {
+            }
+        }
+        // a survivor inside the guard band: float64 must decide
+        if (!(vmin > ylo_in && vmax < yhi_in)) { uncertain = true; break; }
+        if (nk == 0) break;
+        M_prev = fmaxf(M_nf, fmaxf(vmax - c, c - vmin)) * 1.000001f;
+        c_prev = c;
+        const float S2n = S2 - r2;
+        if (S2n >= 0.5f * S2_fresh) {
+            S1 -= r1;
+            S2 = S2n;
+            ++nsub;
+        } else {
+            // rebuild the sums of the survivors from the registers
+            float n1 = 0.f, n2 = 0.f;
+#pragma unroll
+            for (int gidx = 0; gidx < NG; ++gidx) {
                 float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int k = 0; k < GP; ++k) {
@@ -164,11 +193,11 @@ __device__ __forceinline__ void meanclip_pixel(float2 (&y)[NB / 2], const FrameP
                 n1 += s1.x + s1.y;
                 n2 += s2.x + s2.y;
             }
+            S1 = n1;
+            S2 = n2;
+            S2_fresh = n2;
+            nsub = 0;
         }
-        if (uncertain) break;
-        S1 = n1;
-        S2 = n2;
-        if (nk == nk_before || nk == 0) break;
     }
     if (uncertain || nk == 0) { generic_pixel<NB>(fp, a, p); return; }
 
