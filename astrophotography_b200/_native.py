@@ -29,6 +29,7 @@ SIGNATURES = {
     "apgpu_stack_kernel_name": (_c.c_char_p, [
         _c.c_int, _c.c_int, _c.c_double, _c.c_double, _c.c_int, _c.c_int, _c.c_int,
         _c.c_int, _c.c_int, _c.c_int]),
+    "apgpu_stack_last_staging": (_c.c_int, []),
     "apgpu_flat_norm_workspace_bytes": (_c.c_size_t, [_c.c_int64]),
     "apgpu_flat_norm_f32": (_c.c_int, [_P, _c.c_int64, _P, _c.c_size_t, _P, _P]),
     "apgpu_flat_divide_f32": (_c.c_int, [_P, _P, _P, _c.c_int64, _P]),

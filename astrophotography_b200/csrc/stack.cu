@@ -28,6 +28,8 @@
 //                     shared memory for the data-dependent MAD selection.
 //   A pixel holding NaN/inf samples leaves the fast kernels for the generic
 //   routine, which owns the reference's non-finite semantics.
+#include <stdlib.h>
+
 #include "stack_common.cuh"
 
 namespace apgpu_stack {
@@ -83,7 +85,56 @@ int stack_dispatch_meanclip(int nb, const float* const* frames, const StackArgs&
     return stack_dispatch_meanclip_hi(nb, frames, a, st, flags);
 }
 
+bool stack_is_cube(const float* const* frames, int N, int64_t npix_end) {
+    if (N < 2 || N > 256 || npix_end <= 0 || npix_end >= ((int64_t)1 << 31)) return false;
+    const int64_t stride = (const char*)frames[1] - (const char*)frames[0];
+    if (stride < npix_end * (int64_t)sizeof(float) || stride % 16 != 0 || stride >= ((int64_t)1 << 40)) return false;
+    if (!apgpu_aligned(frames[0], 16)) return false;
+    for (int i = 2; i < N; ++i)
+        if ((const char*)frames[i] - (const char*)frames[i - 1] != stride) return false;
+    return true;
+}
+
+bool encode_stack_tensor_map(CUtensorMap* tmap, const float* base, uint64_t npix_end, int N,
+                             uint64_t stride_bytes, int box_pix) {
+    // cuTensorMapEncodeTiled lives in the driver (libcuda): fetched through the runtime so that the
+    // library keeps linking against cudart only
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess || !fn) {
+            (void)cudaGetLastError();
+            return false;
+        }
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    const cuuint64_t gdim[2] = {npix_end, (cuuint64_t)N};
+    const cuuint64_t gstride[1] = {stride_bytes};
+    const cuuint32_t box[2] = {(cuuint32_t)box_pix, (cuuint32_t)N};
+    const cuuint32_t estride[2] = {1, 1};
+    return encode(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estride,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 thread_local char g_kname[64];
+thread_local int g_last_staging = -1;
+void stack_note_staging(int staging) { g_last_staging = staging; }
+int stack_tmap_tiles_per_warp() {
+    // tuning knob (measured on B200, bench.py variants): APGPU_TMAP_TILES_PER_WARP overrides
+    static int v = 0;
+    if (!v) {
+        const char* e = getenv("APGPU_TMAP_TILES_PER_WARP");
+        int x = e ? atoi(e) : 0;
+        v = (x >= 1 && x <= 4096) ? x : 32;
+    }
+    return v;
+}
 
 }  // namespace apgpu_stack
 
@@ -104,6 +155,8 @@ extern "C" const char* apgpu_stack_kernel_name(int N, int method, double k_lo, d
     }
     return g_kname;
 }
+
+extern "C" int apgpu_stack_last_staging(void) { return g_last_staging; }
 
 extern "C" int apgpu_stack_reduce_f32(const float* const* frames, int N, int64_t H, int64_t W,
                                       int64_t row0, int64_t nrows, int method,
@@ -134,6 +187,7 @@ extern "C" int apgpu_stack_reduce_f32(const float* const* frames, int N, int64_t
     a.nrej = out_nrej; a.nrej_u16 = nrej_is_u16;
     a.uncert = out_uncert; a.allmasked = out_allmasked;
     cudaStream_t st = (cudaStream_t)stream;
+    g_last_staging = -1;
 
     const Bucket* b = nullptr;
     Family f = choose_family(N, method, k_lo, k_hi, maxiters, cen, dev, out_uncert != nullptr, flags, &b);

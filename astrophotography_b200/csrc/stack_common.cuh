@@ -32,6 +32,8 @@
 #include <float.h>
 #include <math.h>
 
+#include <cuda.h>
+
 #include "apgpu_common.cuh"
 
 namespace apgpu_stack {
@@ -54,6 +56,7 @@ struct StackArgs {
     // staged kernels zero the rows) and multiply the pivot-shifted value by this mask: no
     // per-sample predicates in the load phase.
     float tailmask[MEANCLIP_MAX_TAIL];
+    int tiles_per_warp;          // tensor-map staged kernel: warp tiles per warp per CTA
 };
 
 template <int CAP> struct FramePtrs { const float* p[CAP]; };
@@ -243,6 +246,16 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gm
 // Threads (= pixels) per CTA of the TMA-staged kernel: 256, so that every bulk copy
 
 struct Bucket { int nb, nlo; };
+
+// Equally spaced frames (a [N][H*W] cube) can be described by one 2-D TMA tensor map.
+bool stack_is_cube(const float* const* frames, int N, int64_t npix_end);
+// dim0 = pixel (npix_end of them, contiguous), dim1 = frame (N, stride_bytes apart); box = box_pix x N.
+bool encode_stack_tensor_map(CUtensorMap* tmap, const float* base, uint64_t npix_end, int N,
+                             uint64_t stride_bytes, int box_pix);
+
+// what the last apgpu_stack_reduce_f32 call of this thread launched (tests / bench bookkeeping)
+void stack_note_staging(int staging);
+int stack_tmap_tiles_per_warp();
 
 // cross-translation-unit launchers (one .cu per kernel family so that nvcc compiles them in parallel)
 int stack_launch_generic(const float* const* frames, const StackArgs& a, cudaStream_t st);

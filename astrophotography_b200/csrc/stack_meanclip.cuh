@@ -34,9 +34,16 @@ constexpr int meanclip_min_blocks(int NB) {
 }
 
 // The per-pixel work, given the N raw samples of pixel p in y[] (padding = 0).
-template <int NB, int NLO, bool SYM>
+constexpr int WT = 32;      // pixels per warp tile of the warp-granular staged kernels
+
+struct NoHook { __device__ __forceinline__ void operator()(float) const {} };
+
+// after_sums(S2) is called once every sample of the pixel has been consumed (the staged kernels
+// re-arm their shared-memory stage there); it runs before any early exit.
+template <int NB, int NLO, bool SYM, typename AfterSums = NoHook>
 __device__ __forceinline__ void meanclip_pixel(float2 (&y)[NB / 2], const FramePtrs<NB>& fp,
-                                               const StackArgs& a, const int64_t p) {
+                                               const StackArgs& a, const int64_t p,
+                                               const AfterSums& after_sums = AfterSums()) {
     static_assert(NB % 2 == 0, "meanclip buckets must be even");
     const int N = a.N;
     constexpr int NP = NB / 2;                         // register pairs
@@ -68,6 +75,7 @@ __device__ __forceinline__ void meanclip_pixel(float2 (&y)[NB / 2], const FrameP
         S1 += s1.x + s1.y;
         S2 += s2.x + s2.y;
     }
+    after_sums(S2);
     // NaN input poisons S1/S2, inf input (or overflow) makes S2 infinite: the
     // generic routine owns those semantics.
     if (!(S2 <= FLT_MAX) || !(fabsf(S1) <= FLT_MAX)) { generic_pixel<NB>(fp, a, p); return; }
@@ -301,6 +309,92 @@ stack_meanclip_tma_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid
 }
 
 // ---------------------------------------------------------------------------
+// Tensor-map TMA staged persistent kernel: one bulk tensor copy per warp tile
+// ---------------------------------------------------------------------------
+// When the N frames are equally spaced in memory (a [N][H*W] cube, which is what the host
+// pipeline and torch cubes are) the whole stack is ONE 2-D tensor: dim0 = pixel, dim1 = frame.
+// Every warp is its own pipeline: it owns a [N][32-pixel] shared-memory stage and an mbarrier;
+// one elected lane issues a single cp.async.bulk.tensor.2d (box = 32 pixels x N frames, 128 B
+// per frame row: UTMALDG in SASS) per tile, the lanes read their column out of the stage
+// (conflict-free LDS with immediate offsets -- no per-sample address arithmetic, no global-load
+// instructions in the instruction stream), and the copy for the warp's NEXT tile is issued
+// as soon as every sample has been consumed, so its HBM latency hides behind the clipping
+// arithmetic of the current tile.  No CTA barrier anywhere.
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* tmap, int32_t c0, int32_t c1,
+                                            uint64_t* bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%2, %3}], [%4], %5;"
+        ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+
+template <int NB, int NLO, bool SYM>
+__global__ void __launch_bounds__(TPB, meanclip_min_blocks(NB))
+stack_meanclip_tmap_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FramePtrs<NB> fp,
+                           const __grid_constant__ StackArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* stage = reinterpret_cast<float*>(smem_raw) + (size_t)warp * NB * WT;          // [NB][32]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)(TPB / 32) * NB * WT * sizeof(float)) + warp;
+    const int N = a.N;
+    if (lane == 0) mbar_init(bar, 1);
+    for (int i = N * WT + lane; i < NB * WT; i += 32) stage[i] = 0.f;         // padding rows: never copied into
+    __syncwarp();
+    const uint64_t policy = l2_evict_first_policy();
+    const uint32_t tile_bytes = (uint32_t)N * WT * sizeof(float);
+    // Each CTA owns a run of 4 * tiles_per_warp consecutive warp tiles (its warps interleave);
+    // the hardware CTA scheduler balances the runs over the SMs (a fully persistent grid with a
+    // static tile assignment left SMs idle 17 % of the time: SMs do not all see the same
+    // memory throughput).
+    const int64_t ntiles = a.npix / WT;                                       // full warp tiles (host launches the tail)
+    const int64_t run = (int64_t)(TPB / 32) * a.tiles_per_warp;
+    int64_t tile = (int64_t)blockIdx.x * run + warp;
+    const int64_t tile_end = (tile - warp + run < ntiles) ? tile - warp + run : ntiles;
+    constexpr int64_t nwarps = TPB / 32;
+    uint32_t parity = 0;
+    if (tile < tile_end && lane == 0) {
+        mbar_expect_tx(bar, tile_bytes);
+        tma_load_2d(stage, &tmap, (int32_t)(a.pix0 + tile * WT), 0, bar, policy);
+    }
+    for (; tile < tile_end; tile += nwarps) {
+        while (!mbar_try_wait(bar, parity)) {}
+        parity ^= 1u;
+        float2 y[NB / 2];
+#pragma unroll
+        for (int j = 0; j < NB / 2; ++j) {
+            y[j].x = stage[(2 * j) * WT + lane];
+            y[j].y = stage[(2 * j + 1) * WT + lane];
+        }
+        const int64_t next = tile + nwarps;
+        // re-arm the stage once the sums (which depend on every staged sample of every lane of
+        // this warp instruction stream) exist: the predicate below carries that dependence
+        auto rearm = [&](float s2) {
+            if (lane == 0 && next < tile_end && s2 != -1.f) {
+                mbar_expect_tx(bar, tile_bytes);
+                tma_load_2d(stage, &tmap, (int32_t)(a.pix0 + next * WT), 0, bar, policy);
+            }
+            __syncwarp();
+        };
+        meanclip_pixel<NB, NLO, SYM>(y, fp, a, a.pix0 + tile * WT + lane, rearm);
+    }
+}
+
+// ---------------------------------------------------------------------------
 // cp.async-staged persistent kernel: warp-granular software pipeline
 // ---------------------------------------------------------------------------
 // Every warp is its own pipeline: it owns a private [N][32-pixel] shared-memory
@@ -318,7 +412,6 @@ __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-constexpr int WT = 32;      // pixels per warp tile
 
 __device__ __forceinline__ void issue_warp_tile(const float* const* ptab, int N, int64_t pix, float* stage, int lane) {
     const int sub = lane >> 3;            // which of the 4 frames of this instruction
@@ -363,8 +456,29 @@ stack_meanclip_cpasync_kernel(const __grid_constant__ FramePtrs<NB> fp, const __
 
 template <int NB, int NLO, bool SYM>
 int launch_meanclip_sym(const FramePtrs<NB>& fp, const StackArgs& a, int staging, cudaStream_t st) {
-    // staging: 0 direct global loads, 1 CTA-wide TMA bulk copies, 2 warp-granular cp.async pipeline
+    // staging: 0 direct global loads, 1 CTA-wide TMA bulk copies, 2 warp-granular cp.async pipeline,
+    //          3 warp-granular tensor-map TMA pipeline (equally spaced frames only)
     StackArgs rest = a;
+    if (staging == 3) {
+        const int64_t ntiles = a.npix / WT;
+        CUtensorMap tmap;
+        const int64_t stride = (const char*)fp.p[1] - (const char*)fp.p[0];
+        if (ntiles > 0 && encode_stack_tensor_map(&tmap, fp.p[0], (uint64_t)(a.pix0 + a.npix), a.N, (uint64_t)stride, WT)) {
+            const size_t smem = (size_t)(TPB / 32) * NB * WT * sizeof(float) + (TPB / 32) * sizeof(uint64_t);
+            APGPU_CUDA(cudaFuncSetAttribute(stack_meanclip_tmap_kernel<NB, NLO, SYM>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            StackArgs at = a;
+            at.tiles_per_warp = stack_tmap_tiles_per_warp();
+            const int64_t run = (int64_t)(TPB / 32) * at.tiles_per_warp;
+            const int64_t grid = (ntiles + run - 1) / run;
+            stack_meanclip_tmap_kernel<NB, NLO, SYM><<<(unsigned)grid, TPB, smem, st>>>(tmap, fp, at);
+            APGPU_LAUNCH_CHECK("stack_meanclip_tmap_kernel");
+            rest.pix0 = a.pix0 + ntiles * WT;            // the < 32-pixel tail goes through the direct kernel
+            rest.npix = a.npix - ntiles * WT;
+        } else {
+            stack_note_staging(0);
+        }
+    }
     if (staging == 2) {
         const int64_t ntiles = a.npix / WT;
         if (ntiles > 0) {
@@ -411,16 +525,24 @@ int launch_meanclip(const float* const* frames, const StackArgs& a_in, cudaStrea
     for (int i = 0; i < NB; ++i) fp.p[i] = i < a_in.N ? frames[i] : frames[0];   // padding: loaded, then masked
     StackArgs a = a_in;
     for (int i = NLO; i < NB; ++i) a.tailmask[i - NLO] = i < a.N ? 1.f : 0.f;
-    // asynchronous copies need 16-byte aligned sources: frame base + first pixel of the band
-    // default (measured, bench.py variants): the warp-granular cp.async pipeline wins for the
-    // shorter stacks (N=30: +8 %), direct loads are level or slightly ahead from N~80 up
-    int staging = (flags & APGPU_STACK_USE_TMA) ? 1 : ((flags & APGPU_STACK_DIRECT_LOADS) ? 0 : (NB <= 64 ? 2 : 0));
+    // staging: 0 direct loads, 1 CTA-wide bulk copies, 2 warp-granular cp.async, 3 warp-granular tensor-map TMA.
+    // Default (measured, bench.py variants / tools/time_variant.py): the tensor-map TMA pipeline wherever the
+    // frames are equally spaced; otherwise cp.async for the shorter stacks and direct loads from N~80 up.
+    int staging = 3;
+    if (flags & APGPU_STACK_USE_TMA) staging = 1;
+    if (flags & APGPU_STACK_DIRECT_LOADS) staging = 0;
     if (flags & APGPU_STACK_USE_CPASYNC) staging = 2;
+    if (flags & APGPU_STACK_USE_TENSORMAP) staging = 3;
+    if (staging == 3 && !stack_is_cube(frames, a.N, a.pix0 + a.npix))
+        staging = (flags & APGPU_STACK_USE_TENSORMAP) ? 0 : (NB <= 64 ? 2 : 0);
     // the per-warp stages must leave room for meanclip_min_blocks CTAs per SM
     const size_t smem_cta = (size_t)NB * sizeof(float*) + (size_t)(TPB / 32) * NB * WT * sizeof(float);
-    if (staging == 2 && smem_cta * meanclip_min_blocks(NB) > (size_t)SMEM_MAX_BYTES) staging = 0;
-    for (int i = 0; i < a.N; ++i)
-        if (!apgpu_aligned(frames[i] + a.pix0, 16)) staging = 0;
+    if ((staging == 2 || staging == 3) && smem_cta * meanclip_min_blocks(NB) > (size_t)SMEM_MAX_BYTES) staging = 0;
+    // asynchronous copies need 16-byte aligned sources: frame base + first pixel of the band
+    if (staging == 1 || staging == 2)
+        for (int i = 0; i < a.N; ++i)
+            if (!apgpu_aligned(frames[i] + a.pix0, 16)) staging = 0;
+    stack_note_staging(staging);
     if ((float)a.klo == (float)a.khi) return launch_meanclip_sym<NB, NLO, true>(fp, a, staging, st);
     return launch_meanclip_sym<NB, NLO, false>(fp, a, staging, st);
 }

@@ -16,7 +16,8 @@ CENFUNCS = {"mean": 0, "median": 1}
 DEVFUNCS = {"std": 0, "mad_std": 1}
 _FORCE_GENERIC = 1
 _PREFER = {None: 0, "registers": 2, "shared": 4, "registers_tma": 2 | 8, "tma": 8,
-           "registers_direct": 2 | 16, "direct": 16, "registers_cpasync": 2 | 32, "cpasync": 32}
+           "registers_direct": 2 | 16, "direct": 16, "registers_cpasync": 2 | 32, "cpasync": 32,
+           "registers_tensormap": 2 | 64, "tensormap": 64}
 
 
 def _stream(torch):
@@ -43,6 +44,11 @@ def stack_kernel_name(n, method="average", k_lo=5.0, k_hi=5.0, maxiters=1, cen="
         int(n), METHODS[method], float(k_lo), float(k_hi), _maxiters(maxiters), CENFUNCS[cen],
         DEVFUNCS[dev], int(want_uncert), int(out_f64),
         (_FORCE_GENERIC if force_generic else 0) | _PREFER[prefer]).decode()
+
+
+def stack_last_staging():
+    """0 direct loads, 1 bulk copies, 2 cp.async, 3 tensor-map TMA, -1 not a meanclip launch."""
+    return int(_native.load().apgpu_stack_last_staging())
 
 
 def _maxiters(maxiters):

@@ -287,6 +287,8 @@ def run_gpu(args, shape):
                     lambda: kernels.stack_reduce(cube, out=out, prefer="registers", **HEADLINE), n * mpix, alg_bytes)
         add_variant("stack_kappa_sigma_registers_cpasync_staged[%s]" % kernels.stack_kernel_name(n, prefer="registers", **HEADLINE),
                     lambda: kernels.stack_reduce(cube, out=out, prefer="registers_cpasync", **HEADLINE), n * mpix, alg_bytes)
+        add_variant("stack_kappa_sigma_registers_tensormap_staged[%s]" % kernels.stack_kernel_name(n, prefer="registers", **HEADLINE),
+                    lambda: kernels.stack_reduce(cube, out=out, prefer="registers_tensormap", **HEADLINE), n * mpix, alg_bytes)
         add_variant("stack_kappa_sigma_registers_tma_staged[%s]" % kernels.stack_kernel_name(n, prefer="registers", **HEADLINE),
                     lambda: kernels.stack_reduce(cube, out=out, prefer="registers_tma", **HEADLINE), n * mpix, alg_bytes)
         add_variant("stack_kappa_sigma_shared[%s]" % kernels.stack_kernel_name(n, prefer="shared", **HEADLINE),

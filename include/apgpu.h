@@ -79,6 +79,7 @@ enum { APGPU_DEV_STD = 0, APGPU_DEV_MAD_STD = 1 };
 #define APGPU_STACK_USE_TMA 8            /* tuning/tests: CTA-wide TMA bulk-copy staging */
 #define APGPU_STACK_DIRECT_LOADS 16      /* tuning/tests: direct global loads, no shared-memory staging */
 #define APGPU_STACK_USE_CPASYNC 32       /* tuning/tests: warp-granular cp.async staging pipeline */
+#define APGPU_STACK_USE_TENSORMAP 64     /* tuning/tests: warp-granular tensor-map TMA staging (equally spaced frames) */
 #define APGPU_STACK_MAX_FRAMES 1024
 
 int apgpu_stack_reduce_f32(const float* const* frames, int N, int64_t H, int64_t W,
@@ -94,6 +95,13 @@ int apgpu_stack_reduce_f32(const float* const* frames, int N, int64_t H, int64_t
 const char* apgpu_stack_kernel_name(int N, int method, double k_lo, double k_hi,
                                     int maxiters, int cen, int dev,
                                     int want_uncert, int out_is_f64, int flags);
+
+/* How the last apgpu_stack_reduce_f32 call of the calling thread fed the
+ * meanclip kernel: -1 not a meanclip launch, 0 direct global loads, 1 CTA-wide
+ * bulk copies, 2 warp-granular cp.async, 3 warp-granular tensor-map TMA.  For
+ * tests and the benchmark's bookkeeping (a requested staging falls back to 0
+ * when its alignment / layout preconditions do not hold). */
+int apgpu_stack_last_staging(void);
 
 /* ------------------------------------------------------------------------
  * Flat normalisation.  Replaces ApCalibrate._generate_flat,

@@ -181,6 +181,29 @@ def test_meanclip_large_n(cuda, n, prefer):
     _assert_close_data(got["uncert"].astype(np.float64), exp["uncert"], 1e-5, 1e-3)
 
 
+@pytest.mark.parametrize("n", [3, 8, 30, 31, 64, 81, 100, 127, 160, 200])
+@pytest.mark.parametrize("case", [c for c in FAST_CASES if c[-1] == "meanclip"], ids=lambda c: "-".join(map(str, c)))
+def test_meanclip_tensormap_staging(cuda, n, case):
+    """Equally spaced frames (a torch cube whose frame size is a multiple of 16 bytes) go through the
+    warp-granular tensor-map TMA pipeline: same results as the oracle, and the path really ran."""
+    torch = cuda
+    from astrophotography_b200 import kernels
+    method, k_lo, k_hi, maxiters, cen, dev, _ = case
+    st = _stack(n, (11, 76), seed=21 + n, quantise=(n % 2 == 1))     # 836 pixels: 26 warp tiles + 4-pixel tail
+    exp = _oracle(st, method, k_lo, k_hi, maxiters, cen, dev)
+    for out_f64 in (False, True):
+        got = _run(torch, st, method=method, k_lo=k_lo, k_hi=k_hi, maxiters=maxiters, cen=cen, dev=dev,
+                   out_f64=out_f64, prefer="registers_tensormap")
+        assert kernels.stack_last_staging() == 3
+        assert np.array_equal(got["nrej"].astype(np.int64), exp["nrej"])
+        assert np.array_equal(got["allmasked"], exp["allmasked"])
+        _assert_close_data(got["data"].astype(np.float64), exp["data"], RTOL32 if not out_f64 else 2e-7, 12.0)
+    # frames that are not 16-byte spaced fall back to direct loads
+    st2 = _stack(n, (9, 70), seed=3)
+    _run(torch, st2, method=method, k_lo=k_lo, k_hi=k_hi, maxiters=maxiters, cen=cen, dev=dev, prefer="registers_tensormap")
+    assert kernels.stack_last_staging() == 0
+
+
 def test_fast_uncert(cuda):
     torch = cuda
     st = _stack(30, (8, 64), seed=5)
