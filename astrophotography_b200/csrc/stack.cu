@@ -55,12 +55,18 @@ const Bucket* find_bucket(const Bucket (&b)[K], int N) {
     return nullptr;
 }
 
+// the kappa-sigma-about-the-mean family (meanclip kernels) handles this parameter set
+bool meanclip_eligible(int N, int method, double klo, double khi, int maxiters, int cen, int dev, int flags) {
+    return !(flags & APGPU_STACK_FORCE_GENERIC) && method == APGPU_METHOD_AVERAGE &&
+           (maxiters == 0 || (cen == APGPU_CEN_MEAN && dev == APGPU_DEV_STD)) &&
+           N >= 3 && klo > 0.0 && khi > 0.0 && klo < 1e6 && khi < 1e6;
+}
+
 Family choose_family(int N, int method, double klo, double khi, int maxiters, int cen, int dev,
                      bool want_uncert, int flags, const Bucket** bucket) {
     *bucket = nullptr;
     if (flags & APGPU_STACK_FORCE_GENERIC) return FAM_GENERIC;
-    if (method == APGPU_METHOD_AVERAGE && (maxiters == 0 || (cen == APGPU_CEN_MEAN && dev == APGPU_DEV_STD)) &&
-        N >= 3 && klo > 0.0 && khi > 0.0 && klo < 1e6 && khi < 1e6) {
+    if (meanclip_eligible(N, method, klo, khi, maxiters, cen, dev, flags)) {
         const Bucket* rb = find_bucket(MEANCLIP_BUCKETS, N);
         const bool smem_ok = N <= MEANCLIP_SMEM_MAX_N;
         bool use_reg = rb && (N <= MEANCLIP_REG_DEFAULT_MAX_N || !smem_ok);
@@ -79,14 +85,48 @@ Family choose_family(int N, int method, double klo, double khi, int maxiters, in
     return FAM_GENERIC;
 }
 
+int stack_dispatch_meanclip_split(const float* const* frames, const StackArgs& a, cudaStream_t st, int flags,
+                                  int64_t* done_pix) {
+    *done_pix = 0;
+    if (flags & (APGPU_STACK_DIRECT_LOADS | APGPU_STACK_USE_TMA | APGPU_STACK_USE_CPASYNC | APGPU_STACK_PREFER_SHARED |
+                 APGPU_STACK_PREFER_REGISTERS))
+        return APGPU_ERR_UNSUPPORTED;
+    if (!stack_is_cube(frames, a.N, a.pix0 + a.npix)) return APGPU_ERR_UNSUPPORTED;
+    static const bool no_coop = getenv("APGPU_NO_COOP") != nullptr;           // dev tuning
+    if (!no_coop && a.N <= 512) {
+        // lanes per pixel (measured, tools/time_variant.py): short per-lane arrays (<= 64 samples) keep the
+        // unrolled code and the register count small, which matters more than the extra shuffle steps
+        static const int force_p = getenv("APGPU_COOP_P") ? atoi(getenv("APGPU_COOP_P")) : 0;   // dev tuning
+        int P = a.N <= 128 ? 2 : (a.N <= 256 ? 4 : 8);
+        if (force_p) P = force_p;
+        int rc = APGPU_ERR_UNSUPPORTED;
+        if (P == 2) rc = stack_dispatch_meanclip_coop_p2(frames, a, st, done_pix);
+        if (P == 4) rc = stack_dispatch_meanclip_coop_p4(frames, a, st, done_pix);
+        if (P == 8) rc = stack_dispatch_meanclip_coop_p8(frames, a, st, done_pix);
+        if (rc != APGPU_ERR_UNSUPPORTED) return rc;
+    }
+    if (a.N <= 200) return stack_dispatch_meanclip_split_p2(frames, a, st, done_pix);
+    if (a.N <= 512) return stack_dispatch_meanclip_split_p4(frames, a, st, done_pix);
+    return stack_dispatch_meanclip_split_p8(frames, a, st, done_pix);
+}
+
 int stack_dispatch_meanclip(int nb, const float* const* frames, const StackArgs& a, cudaStream_t st, int flags) {
     if (nb <= 64) return stack_dispatch_meanclip_lo(nb, frames, a, st, flags);
     if (nb <= 128) return stack_dispatch_meanclip_mid(nb, frames, a, st, flags);
     return stack_dispatch_meanclip_hi(nb, frames, a, st, flags);
 }
 
+int stack_coop_box_rows_max() {
+    static int v = 0;
+    if (!v) {
+        const char* e = getenv("APGPU_COOP_BOX_ROWS");      // tuning knob
+        int x = e ? atoi(e) : 0;
+        v = (x >= 8 && x <= 256) ? x : 256;
+    }
+    return v;
+}
 bool stack_is_cube(const float* const* frames, int N, int64_t npix_end) {
-    if (N < 2 || N > 256 || npix_end <= 0 || npix_end >= ((int64_t)1 << 31)) return false;
+    if (N < 2 || npix_end <= 0 || npix_end >= ((int64_t)1 << 31)) return false;
     const int64_t stride = (const char*)frames[1] - (const char*)frames[0];
     if (stride < npix_end * (int64_t)sizeof(float) || stride % 16 != 0 || stride >= ((int64_t)1 << 40)) return false;
     if (!apgpu_aligned(frames[0], 16)) return false;
@@ -96,7 +136,7 @@ bool stack_is_cube(const float* const* frames, int N, int64_t npix_end) {
 }
 
 bool encode_stack_tensor_map(CUtensorMap* tmap, const float* base, uint64_t npix_end, int N,
-                             uint64_t stride_bytes, int box_pix) {
+                             uint64_t stride_bytes, int box_pix, int box_rows, bool swizzle128) {
     // cuTensorMapEncodeTiled lives in the driver (libcuda): fetched through the runtime so that the
     // library keeps linking against cudart only
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -115,10 +155,10 @@ bool encode_stack_tensor_map(CUtensorMap* tmap, const float* base, uint64_t npix
     }
     const cuuint64_t gdim[2] = {npix_end, (cuuint64_t)N};
     const cuuint64_t gstride[1] = {stride_bytes};
-    const cuuint32_t box[2] = {(cuuint32_t)box_pix, (cuuint32_t)N};
+    const cuuint32_t box[2] = {(cuuint32_t)box_pix, (cuuint32_t)(box_rows > 0 ? box_rows : N)};
     const cuuint32_t estride[2] = {1, 1};
     return encode(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estride,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -189,8 +229,24 @@ extern "C" int apgpu_stack_reduce_f32(const float* const* frames, int N, int64_t
     cudaStream_t st = (cudaStream_t)stream;
     g_last_staging = -1;
 
+    // long stacks on equally spaced frames: the lane-split tensor-map kernels take every full warp tile,
+    // whatever follows only sees the (< 32-pixel) tail
+    static const bool split_100 = getenv("APGPU_SPLIT_100") != nullptr;         // dev tuning
+    if (N > (split_100 ? 80 : 100) && meanclip_eligible(N, method, k_lo, k_hi, maxiters, cen, dev, flags)) {
+        int64_t done = 0;
+        const int rc = stack_dispatch_meanclip_split(frames, a, st, flags, &done);
+        if (rc != APGPU_OK && rc != APGPU_ERR_UNSUPPORTED) return rc;
+        if (rc == APGPU_OK) {
+            a.pix0 += done;
+            a.npix -= done;
+            if (a.npix == 0) return APGPU_OK;
+        }
+    }
+    const int staging_so_far = g_last_staging;
+
     const Bucket* b = nullptr;
     Family f = choose_family(N, method, k_lo, k_hi, maxiters, cen, dev, out_uncert != nullptr, flags, &b);
+    struct Restore { int v; ~Restore() { if (v >= 0) g_last_staging = v; } } restore{staging_so_far};
     switch (f) {
         case FAM_MEANCLIP: return stack_dispatch_meanclip(b->nb, frames, a, st, flags);
         case FAM_MEANCLIP_SMEM:

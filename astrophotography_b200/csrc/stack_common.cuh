@@ -56,10 +56,22 @@ struct StackArgs {
     // staged kernels zero the rows) and multiply the pivot-shifted value by this mask: no
     // per-sample predicates in the load phase.
     float tailmask[MEANCLIP_MAX_TAIL];
-    int tiles_per_warp;          // tensor-map staged kernel: warp tiles per warp per CTA
+    int tiles_per_warp;          // tensor-map staged kernels: warp tiles per warp (per group) per CTA
+    int box_rows, nchunks;       // warp-cooperative kernel: rows per TMA box, boxes per tile
 };
 
-template <int CAP> struct FramePtrs { const float* p[CAP]; };
+template <int CAP> struct FramePtrs {
+    const float* p[CAP];
+    __device__ __forceinline__ const float* frame(int i) const { return p[i]; }
+};
+// equally spaced frames (a [N][H*W] cube): frame i starts stride bytes after frame i-1
+struct CubeFrames {
+    const char* base;
+    int64_t stride;
+    __device__ __forceinline__ const float* frame(int i) const {
+        return reinterpret_cast<const float*>(base + (int64_t)i * stride);
+    }
+};
 
 __device__ __forceinline__ bool finite_f(float x) { return fabsf(x) <= FLT_MAX; }
 
@@ -125,8 +137,8 @@ __device__ __forceinline__ double mad_sorted(const float* s, int sa, int sb, dou
     return (m & 1) ? d1 : __dmul_rn(__dadd_rn(d1, d2), 0.5);
 }
 
-template <int CAP>
-__device__ __noinline__ void generic_pixel(const FramePtrs<CAP>& fp, const StackArgs& a, int64_t p) {
+template <int CAP, typename Frames = FramePtrs<CAP>>
+__device__ __noinline__ void generic_pixel(const Frames& fp, const StackArgs& a, int64_t p) {
     float v[CAP];      // frame order; NaN marks a sample that is not (or no longer) used
     float s[CAP];      // the used samples, ascending
     const int N = a.N;
@@ -135,7 +147,7 @@ __device__ __noinline__ void generic_pixel(const FramePtrs<CAP>& fp, const Stack
                              (clip && (a.cen == APGPU_CEN_MEDIAN || a.dev == APGPU_DEV_MAD_STD));
     int nk = 0;
     for (int i = 0; i < N; ++i) {
-        float x = ld_stream(fp.p[i] + p);
+        float x = ld_stream(fp.frame(i) + p);
         // sigma_clip rejects non-finite samples up front; without clipping the
         // nan-functions only skip NaN.
         bool ok = clip ? finite_f(x) : (x == x);
@@ -249,13 +261,15 @@ struct Bucket { int nb, nlo; };
 
 // Equally spaced frames (a [N][H*W] cube) can be described by one 2-D TMA tensor map.
 bool stack_is_cube(const float* const* frames, int N, int64_t npix_end);
-// dim0 = pixel (npix_end of them, contiguous), dim1 = frame (N, stride_bytes apart); box = box_pix x N.
+// dim0 = pixel (npix_end of them, contiguous), dim1 = frame (N, stride_bytes apart); box = box_pix x box_rows
+// (box_rows = 0: all N frames in one box, N <= 256).
 bool encode_stack_tensor_map(CUtensorMap* tmap, const float* base, uint64_t npix_end, int N,
-                             uint64_t stride_bytes, int box_pix);
+                             uint64_t stride_bytes, int box_pix, int box_rows = 0, bool swizzle128 = false);
 
 // what the last apgpu_stack_reduce_f32 call of this thread launched (tests / bench bookkeeping)
 void stack_note_staging(int staging);
 int stack_tmap_tiles_per_warp();
+int stack_coop_box_rows_max();
 
 // cross-translation-unit launchers (one .cu per kernel family so that nvcc compiles them in parallel)
 int stack_launch_generic(const float* const* frames, const StackArgs& a, cudaStream_t st);
@@ -264,6 +278,16 @@ int stack_dispatch_meanclip_lo(int nb, const float* const* frames, const StackAr
 int stack_dispatch_meanclip_mid(int nb, const float* const* frames, const StackArgs& a, cudaStream_t st, int flags);
 int stack_dispatch_meanclip_hi(int nb, const float* const* frames, const StackArgs& a, cudaStream_t st, int flags);
 int stack_launch_meanclip_smem(const float* const* frames, const StackArgs& a, cudaStream_t st);
+// lane-split tensor-map kernels (N > 100 on equally spaced frames): returns APGPU_ERR_UNSUPPORTED when there
+// is no bucket; *done_pix = pixels (from a.pix0) that were reduced, the caller finishes the tail
+int stack_dispatch_meanclip_split(const float* const* frames, const StackArgs& a, cudaStream_t st, int flags,
+                                  int64_t* done_pix);
+int stack_dispatch_meanclip_split_p2(const float* const* frames, const StackArgs& a, cudaStream_t st, int64_t* done_pix);
+int stack_dispatch_meanclip_split_p4(const float* const* frames, const StackArgs& a, cudaStream_t st, int64_t* done_pix);
+int stack_dispatch_meanclip_split_p8(const float* const* frames, const StackArgs& a, cudaStream_t st, int64_t* done_pix);
+int stack_dispatch_meanclip_coop_p2(const float* const* frames, const StackArgs& a, cudaStream_t st, int64_t* done_pix);
+int stack_dispatch_meanclip_coop_p4(const float* const* frames, const StackArgs& a, cudaStream_t st, int64_t* done_pix);
+int stack_dispatch_meanclip_coop_p8(const float* const* frames, const StackArgs& a, cudaStream_t st, int64_t* done_pix);
 int stack_dispatch_sorted_med(int nb, const float* const* frames, const StackArgs& a, cudaStream_t st);
 int stack_dispatch_sorted_medmad1(int nb, const float* const* frames, const StackArgs& a, cudaStream_t st);
 

@@ -38,13 +38,69 @@ constexpr int WT = 32;      // pixels per warp tile of the warp-granular staged 
 
 struct NoHook { __device__ __forceinline__ void operator()(float) const {} };
 
+// P lanes of a warp share one pixel (lane = r * (32/P) + q holds the samples i = P*j + r of pixel q):
+// butterfly all-reductions over those lanes.  Every lane of the group ends up with the identical
+// value (the operations are commutative), so the lanes take identical decisions.  P = 1: no-ops.
+// Which frame does sample j of lane r (of the P lanes of a pixel) hold?
+template <int P> struct InterleavedFrames {            // i = P*j + r
+    static __device__ __forceinline__ constexpr int idx(int j, int r) { return P * j + r; }
+};
+template <int P> struct SwizzledFrames {               // i = 8*(j / RB) + RB*r + j % RB, RB = 8/P (see stack_meanclip_coop.cuh)
+    static constexpr int RB = 8 / P;
+    static __device__ __forceinline__ constexpr int idx(int j, int r) { return 8 * (j / RB) + RB * r + j % RB; }
+};
+
+template <int P> struct LaneGroup {
+    static constexpr int PIXW = 32 / P;
+    static __device__ __forceinline__ float sum(float v, unsigned m) {
+#pragma unroll
+        for (int o = PIXW; o < 32; o <<= 1) v += __shfl_xor_sync(m, v, o);
+        return v;
+    }
+    static __device__ __forceinline__ double sum(double v, unsigned m) {
+#pragma unroll
+        for (int o = PIXW; o < 32; o <<= 1) v = __dadd_rn(v, __shfl_xor_sync(m, v, o));
+        return v;
+    }
+    static __device__ __forceinline__ int sum(int v, unsigned m) {
+#pragma unroll
+        for (int o = PIXW; o < 32; o <<= 1) v += __shfl_xor_sync(m, v, o);
+        return v;
+    }
+    static __device__ __forceinline__ float max(float v, unsigned m) {
+#pragma unroll
+        for (int o = PIXW; o < 32; o <<= 1) v = fmaxf(v, __shfl_xor_sync(m, v, o));
+        return v;
+    }
+    static __device__ __forceinline__ float min(float v, unsigned m) {
+#pragma unroll
+        for (int o = PIXW; o < 32; o <<= 1) v = fminf(v, __shfl_xor_sync(m, v, o));
+        return v;
+    }
+    static __device__ __forceinline__ bool any(bool b, unsigned m) {
+        int v = b ? 1 : 0;
+#pragma unroll
+        for (int o = PIXW; o < 32; o <<= 1) v |= __shfl_xor_sync(m, v, o);
+        return v != 0;
+    }
+};
+
 // after_sums(S2) is called once every sample of the pixel has been consumed (the staged kernels
 // re-arm their shared-memory stage there); it runs before any early exit.
-template <int NB, int NLO, bool SYM, typename AfterSums = NoHook>
-__device__ __forceinline__ void meanclip_pixel(float2 (&y)[NB / 2], const FramePtrs<NB>& fp,
+//
+// NB samples per lane; with P > 1 lanes per pixel the stack holds up to NB * P frames, NLO is the
+// bucket's lower bound on the TOTAL frame count, `pivot_in` the pixel's pivot, `gmask` the lanes of
+// the pixel and `r` this lane's index among them (only r == 0 writes / runs the generic fallback).
+template <int NB, int NLO, bool SYM, typename AfterSums = NoHook, int P = 1, typename Frames = FramePtrs<NB>,
+          typename IMap = InterleavedFrames<P>>
+__device__ __forceinline__ void meanclip_pixel(float2 (&y)[NB / 2], const Frames& fp,
                                                const StackArgs& a, const int64_t p,
-                                               const AfterSums& after_sums = AfterSums()) {
+                                               const AfterSums& after_sums = AfterSums(),
+                                               const float pivot_in = 0.f, const unsigned gmask = 0xffffffffu,
+                                               const int r = 0) {
     static_assert(NB % 2 == 0, "meanclip buckets must be even");
+    using G = LaneGroup<P>;
+    constexpr int CAPG = NB * P;                       // capacity of the generic fallback
     const int N = a.N;
     constexpr int NP = NB / 2;                         // register pairs
     constexpr int GP = 4;                              // pairs (8 samples) per group
@@ -54,7 +110,7 @@ __device__ __forceinline__ void meanclip_pixel(float2 (&y)[NB / 2], const FrameP
     // Pivot: median of the first three frames (robust to one outlier).  All
     // float32 arithmetic below is on y = x - pivot: sums stay small and the
     // variance is free of catastrophic cancellation.
-    const float pivot = med3(y[0].x, y[0].y, y[1].x);
+    const float pivot = (P == 1) ? med3(y[0].x, y[0].y, y[1].x) : pivot_in;
     const float2 negpiv = make_float2(-pivot, -pivot);
     float S1 = 0.f, S2 = 0.f;
 #pragma unroll
@@ -65,8 +121,14 @@ __device__ __forceinline__ void meanclip_pixel(float2 (&y)[NB / 2], const FrameP
             const int j = gidx * GP + k;
             if (j < NP) {
                 float2 d = __fadd2_rn(y[j], negpiv);
-                if (2 * j >= NLO)                          // bucket tail: padding beyond N becomes y = 0
-                    d = __fmul2_rn(d, make_float2(a.tailmask[2 * j - NLO], a.tailmask[2 * j + 1 - NLO]));
+                if constexpr (P == 1) {
+                    if (2 * j >= NLO)                      // bucket tail: padding beyond N becomes y = 0
+                        d = __fmul2_rn(d, make_float2(a.tailmask[2 * j - NLO], a.tailmask[2 * j + 1 - NLO]));
+                } else {
+                    // only the top of the bucket can lie beyond N (frame index of sample j of lane r: IMap)
+                    if (IMap::idx(2 * j, P - 1) > NLO && !(IMap::idx(2 * j, r) < N)) d.x = 0.f;
+                    if (IMap::idx(2 * j + 1, P - 1) > NLO && !(IMap::idx(2 * j + 1, r) < N)) d.y = 0.f;
+                }
                 y[j] = d;
                 s1 = __fadd2_rn(s1, d);
                 s2 = __ffma2_rn(d, d, s2);
@@ -76,14 +138,22 @@ __device__ __forceinline__ void meanclip_pixel(float2 (&y)[NB / 2], const FrameP
         S2 += s2.x + s2.y;
     }
     after_sums(S2);
+    constexpr unsigned FULL = 0xffffffffu;
+    if constexpr (P > 1) {
+        S1 = G::sum(S1, FULL);
+        S2 = G::sum(S2, FULL);
+    }
     // NaN input poisons S1/S2, inf input (or overflow) makes S2 infinite: the
     // generic routine owns those semantics.
-    if (!(S2 <= FLT_MAX) || !(fabsf(S1) <= FLT_MAX)) { generic_pixel<NB>(fp, a, p); return; }
+    const bool nonfinite = !(S2 <= FLT_MAX) || !(fabsf(S1) <= FLT_MAX);
+    if constexpr (P == 1) {
+        if (nonfinite) { generic_pixel<CAPG, Frames>(fp, a, p); return; }
+    }
 
     int nk = N;
     const float klo = (float)a.klo, khi = (float)a.khi;
     const float kmax = fmaxf(klo, khi);
-    bool uncertain = false;
+    bool uncertain = nonfinite;
     int it = 0;
     // Sums after a rejection are updated by SUBTRACTING the rejected samples' contributions
     // while that is accurate (what is left of sum(y^2) is at least half of the last fully
@@ -96,36 +166,43 @@ __device__ __forceinline__ void meanclip_pixel(float2 (&y)[NB / 2], const FrameP
     // M_prev + |c - c_prev| is below the new inner bound, every survivor is certainly inside
     // the new clip limits: converged without another pass over the samples.
     float M_prev = -1.f, c_prev = 0.f;
-    while (a.maxiters != 0 && (a.maxiters < 0 || it < a.maxiters)) {
-        ++it;
-        if (S2 == 0.f) break;            // all survivors equal the pivot: bounds [c,c], nothing to reject
+
+    // clip bounds of one iteration, all in the pivot-shifted frame
+    struct Bounds { float c, t_in, lo_in, hi_in, ylo_out, ylo_in, yhi_in, yhi_out; };
+    // returns 0: bounds ready, 1: float64 must decide (degenerate / pivot outside), 2: converged without a pass
+    auto make_bounds = [&](Bounds& B) -> int {
         const float fn = (float)nk;
         const float c = S1 / fn;
         const float ex2 = S2 / fn;
         const float var = ex2 - c * c;
         const float sd = sqrtf(fmaxf(var, 0.f));
         // Bound on |threshold_f32 - threshold_exact| + |y_f32 - y_exact|:
-        // group-wise summation (GP + 1 + NG terms deep), unit roundoff doubled for safety;
-        // after nsub subtractive updates the summation error is relative to sums up to twice
-        // as large, plus one rounding per subtraction.
+        // group-wise summation (GP + 1 + NG terms deep, + log2 P butterfly steps), unit roundoff
+        // doubled for safety; after nsub subtractive updates the summation error is relative to
+        // sums up to twice as large, plus one rounding per subtraction.
         const float u2 = 1.1920929e-7f;                       // 2^-23
-        const float m = (float)(GP + NG + 9) + (nsub ? (float)(GP + NG + 9 + 2 * nsub) : 0.f);
+        constexpr int M0 = GP + NG + 9 + (P > 1 ? 4 : 0);
+        const float m = (float)M0 + (nsub ? (float)(M0 + 2 * nsub) : 0.f);
         const float g = m * u2 * (sqrtf(ex2) + 1.5f * kmax * ex2 / sd) + 6.f * u2 * (fabsf(c) + kmax * sd);
-        if (!(g < 0.25f * kmax * sd)) { uncertain = true; break; }   // degenerate (var ~ 0): let float64 decide
+        if (!(g < 0.25f * kmax * sd)) return 1;               // degenerate (var ~ 0): let float64 decide
         // inner (certainly kept inside) and outer (certainly rejected outside) bounds on t = y - c
-        const float lo_in = -klo * sd + g, lo_out = -klo * sd - g;
-        const float hi_in = khi * sd - g, hi_out = khi * sd + g;
-        const float t_in = fminf(-lo_in, hi_in);              // symmetric inner bound on |t|
-        const float ylo_out = c + lo_out, ylo_in = c + lo_in, yhi_in = c + hi_in, yhi_out = c + hi_out;
+        B.c = c;
+        B.lo_in = -klo * sd + g;
+        B.hi_in = khi * sd - g;
+        const float lo_out = -klo * sd - g, hi_out = khi * sd + g;
+        B.t_in = fminf(-B.lo_in, B.hi_in);                    // symmetric inner bound on |t|
+        B.ylo_out = c + lo_out; B.ylo_in = c + B.lo_in; B.yhi_in = c + B.hi_in; B.yhi_out = c + hi_out;
         // A rejected sample is overwritten with y = 0 (the pivot), so the pivot itself must sit
         // strictly inside the inner bounds: then zeros are never rejected (again) and add nothing.
-        if (!(ylo_in < 0.f && yhi_in > 0.f)) { uncertain = true; break; }
-        if (M_prev >= 0.f && (M_prev + fabsf(c - c_prev)) * 1.000002f < t_in) break;   // converged, no pass needed
-        const float2 negc = make_float2(-c, -c);
-        uint64_t flags = 0;              // bit g: group g holds a sample outside the inner bounds
-        float M_nf = 0.f;                // max |y - c| over the groups that are not flagged
-        // test pass: tight straight-line code, no per-sample predicates, no sums (the sums of
-        // the survivors only change when something is rejected)
+        if (!(B.ylo_in < 0.f && B.yhi_in > 0.f)) return 1;
+        if (M_prev >= 0.f && (M_prev + fabsf(c - c_prev)) * 1.000002f < B.t_in) return 2;
+        return 0;
+    };
+    // test pass: tight straight-line code, no per-sample predicates, no sums (the sums of the
+    // survivors only change when something is rejected).  flags bit g: group g holds a sample
+    // outside the inner bounds; M_nf: max |y - c| over the groups that are not flagged.
+    auto test_pass = [&](const Bounds& B, uint64_t& flags, float& M_nf) {
+        const float2 negc = make_float2(-B.c, -B.c);
 #pragma unroll
         for (int gidx = 0; gidx < NG; ++gidx) {
             float tmax = 0.f, tmin = 0.f;
@@ -142,15 +219,16 @@ __device__ __forceinline__ void meanclip_pixel(float2 (&y)[NB / 2], const FrameP
                     }
                 }
             }
-            const bool flagged = SYM ? (tmax >= t_in) : (tmax >= hi_in || tmin <= lo_in);
+            const bool flagged = SYM ? (tmax >= B.t_in) : (tmax >= B.hi_in || tmin <= B.lo_in);
             if (flagged) flags |= (uint64_t)1 << gidx;
             const float tabs = SYM ? tmax : fmaxf(tmax, -tmin);
             M_nf = fmaxf(M_nf, flagged ? 0.f : tabs);
         }
-        if (flags == 0) break;           // every survivor is certainly inside the bounds: converged
-        // rejection pass over the flagged groups, sample by sample
-        float r1 = 0.f, r2 = 0.f;        // sums over the samples rejected in this iteration
-        float vmax = 0.f, vmin = 0.f;    // range of the survivors (and zeros) of the flagged groups
+    };
+    // rejection pass over the flagged groups, sample by sample: r1, r2 sums over the samples
+    // rejected now, [vmin, vmax] range of the survivors (and zeros) of the flagged groups
+    auto rare_pass = [&](const Bounds& B, const uint64_t flags, float& r1, float& r2, int& nrej_it,
+                         float& vmax, float& vmin) {
 #pragma unroll
         for (int gidx = 0; gidx < NG; ++gidx) {
             if ((flags >> gidx) & 1) {
@@ -161,8 +239,8 @@ __device__ __forceinline__ void meanclip_pixel(float2 (&y)[NB / 2], const FrameP
                         // compare y against bounds shifted by c (not t = y - c: keeps the
                         // compiler from holding every t of the test pass live in registers)
                         const float v = (i & 1) ? y[i >> 1].y : y[i >> 1].x;
-                        const bool keep = (v >= ylo_out) && (v <= yhi_out);
-                        nk -= keep ? 0 : 1;                      // certainly rejected
+                        const bool keep = (v >= B.ylo_out) && (v <= B.yhi_out);
+                        nrej_it += keep ? 0 : 1;                 // certainly rejected
                         const float vr = keep ? 0.f : v;
                         const float vk = keep ? v : 0.f;
                         if (i & 1) y[i >> 1].y = vk; else y[i >> 1].x = vk;
@@ -174,40 +252,117 @@ __device__ __forceinline__ void meanclip_pixel(float2 (&y)[NB / 2], const FrameP
                 }
             }
         }
-        // a survivor inside the guard band: float64 must decide
-        if (!(vmin > ylo_in && vmax < yhi_in)) { uncertain = true; break; }
-        if (nk == 0) break;
-        M_prev = fmaxf(M_nf, fmaxf(vmax - c, c - vmin)) * 1.000001f;
-        c_prev = c;
-        const float S2n = S2 - r2;
-        if (S2n >= 0.5f * S2_fresh) {
-            S1 -= r1;
-            S2 = S2n;
-            ++nsub;
-        } else {
-            // rebuild the sums of the survivors from the registers
-            float n1 = 0.f, n2 = 0.f;
+    };
+    // rebuild the sums of the survivors from the registers
+    auto resum = [&](float& n1, float& n2) {
 #pragma unroll
-            for (int gidx = 0; gidx < NG; ++gidx) {
-                float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
+        for (int gidx = 0; gidx < NG; ++gidx) {
+            float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int k = 0; k < GP; ++k) {
-                    const int j = gidx * GP + k;
-                    if (j < NP) {
-                        s1 = __fadd2_rn(s1, y[j]);
-                        s2 = __ffma2_rn(y[j], y[j], s2);
-                    }
+            for (int k = 0; k < GP; ++k) {
+                const int j = gidx * GP + k;
+                if (j < NP) {
+                    s1 = __fadd2_rn(s1, y[j]);
+                    s2 = __ffma2_rn(y[j], y[j], s2);
                 }
-                n1 += s1.x + s1.y;
-                n2 += s2.x + s2.y;
             }
-            S1 = n1;
-            S2 = n2;
-            S2_fresh = n2;
-            nsub = 0;
+            n1 += s1.x + s1.y;
+            n2 += s2.x + s2.y;
+        }
+    };
+
+    if constexpr (P == 1) {
+        while (a.maxiters != 0 && (a.maxiters < 0 || it < a.maxiters)) {
+            ++it;
+            if (S2 == 0.f) break;            // all survivors equal the pivot: bounds [c,c], nothing to reject
+            Bounds B;
+            const int st = make_bounds(B);
+            if (st == 1) { uncertain = true; break; }
+            if (st == 2) break;              // converged, no pass needed
+            uint64_t flags = 0;
+            float M_nf = 0.f;
+            test_pass(B, flags, M_nf);
+            if (flags == 0) break;           // every survivor is certainly inside the bounds: converged
+            float r1 = 0.f, r2 = 0.f, vmax = 0.f, vmin = 0.f;
+            int nrej_it = 0;
+            rare_pass(B, flags, r1, r2, nrej_it, vmax, vmin);
+            nk -= nrej_it;
+            // a survivor inside the guard band: float64 must decide
+            if (!(vmin > B.ylo_in && vmax < B.yhi_in)) { uncertain = true; break; }
+            if (nk == 0) break;
+            M_prev = fmaxf(M_nf, fmaxf(vmax - B.c, B.c - vmin)) * 1.000001f;
+            c_prev = B.c;
+            const float S2n = S2 - r2;
+            if (S2n >= 0.5f * S2_fresh) {
+                S1 -= r1;
+                S2 = S2n;
+                ++nsub;
+            } else {
+                float n1 = 0.f, n2 = 0.f;
+                resum(n1, n2);
+                S1 = n1;
+                S2 = n2;
+                S2_fresh = n2;
+                nsub = 0;
+            }
+        }
+        if (uncertain || nk == 0) { generic_pixel<CAPG, Frames>(fp, a, p); return; }
+    } else {
+        // P lanes per pixel: the loop is WARP-uniform (every lane stays in it until the warp's last
+        // pixel is done, finished pixels idle through it) so that the butterflies are full-mask
+        // shuffles at fixed points of a converged instruction stream.
+        bool done = (a.maxiters == 0) || nonfinite;
+        for (;;) {
+            const bool act = !done && (a.maxiters < 0 || it < a.maxiters);
+            if (!__any_sync(FULL, act)) break;
+            done = !act;
+            bool pass = false;
+            Bounds B;
+            B.c = 0.f; B.t_in = 0.f; B.lo_in = 0.f; B.hi_in = 0.f; B.ylo_out = 0.f; B.ylo_in = 0.f; B.yhi_in = 0.f; B.yhi_out = 0.f;
+            if (act) {
+                ++it;
+                if (S2 == 0.f) {
+                    done = true;
+                } else {
+                    const int st = make_bounds(B);
+                    if (st == 1) { uncertain = true; done = true; }
+                    else if (st == 2) done = true;
+                    else pass = true;
+                }
+            }
+            uint64_t flags = 0;
+            float M_nf = 0.f;
+            if (pass) test_pass(B, flags, M_nf);
+            const bool anyf = G::any(flags != 0, FULL);
+            M_nf = G::max(M_nf, FULL);
+            if (pass && !anyf) { done = true; pass = false; }
+            float r1 = 0.f, r2 = 0.f, vmax = 0.f, vmin = 0.f;
+            int nrej_it = 0;
+            if (pass) rare_pass(B, flags, r1, r2, nrej_it, vmax, vmin);
+            r1 = G::sum(r1, FULL); r2 = G::sum(r2, FULL); nrej_it = G::sum(nrej_it, FULL);
+            vmax = G::max(vmax, FULL); vmin = G::min(vmin, FULL);
+            bool need_resum = false;
+            if (pass) {
+                nk -= nrej_it;
+                if (!(vmin > B.ylo_in && vmax < B.yhi_in)) { uncertain = true; done = true; }
+                else if (nk == 0) done = true;
+                else {
+                    M_prev = fmaxf(M_nf, fmaxf(vmax - B.c, B.c - vmin)) * 1.000001f;
+                    c_prev = B.c;
+                    const float S2n = S2 - r2;
+                    if (S2n >= 0.5f * S2_fresh) { S1 -= r1; S2 = S2n; ++nsub; }
+                    else need_resum = true;
+                }
+            }
+            if (__any_sync(FULL, need_resum)) {
+                float n1 = 0.f, n2 = 0.f;
+                resum(n1, n2);
+                n1 = G::sum(n1, FULL);
+                n2 = G::sum(n2, FULL);
+                if (need_resum) { S1 = n1; S2 = n2; S2_fresh = n2; nsub = 0; }
+            }
         }
     }
-    if (uncertain || nk == 0) { generic_pixel<NB>(fp, a, p); return; }
 
     // mean of the survivors = pivot + sum(y)/nk (rejected samples are zeros).
     // float32 output: the float32 sums of the small shifted values are accurate
@@ -223,6 +378,14 @@ __device__ __forceinline__ void meanclip_pixel(float2 (&y)[NB / 2], const FrameP
             sum1 = __dadd_rn(__dadd_rn(sum1, d0), d1);
             sum2 = __dadd_rn(__dadd_rn(sum2, __dmul_rn(d0, d0)), __dmul_rn(d1, d1));
         }
+        if constexpr (P > 1) {
+            sum1 = G::sum(sum1, FULL);
+            sum2 = G::sum(sum2, FULL);
+        }
+    }
+    if constexpr (P > 1) {
+        if (r != 0) return;
+        if (uncertain || nk == 0) { generic_pixel<CAPG, Frames>(fp, a, p); return; }
     }
     const double cy = __ddiv_rn(sum1, (double)nk);
     const double mean = __dadd_rn((double)pivot, cy);
@@ -356,7 +519,12 @@ stack_meanclip_tmap_kernel(const __grid_constant__ CUtensorMap tmap, const __gri
     for (int i = N * WT + lane; i < NB * WT; i += 32) stage[i] = 0.f;         // padding rows: never copied into
     __syncwarp();
     const uint64_t policy = l2_evict_first_policy();
+    // one box = the whole tile (cutting it into several concurrent boxes was measured: no gain)
     const uint32_t tile_bytes = (uint32_t)N * WT * sizeof(float);
+    auto issue = [&](int64_t t) {
+        mbar_expect_tx(bar, tile_bytes);
+        tma_load_2d(stage, &tmap, (int32_t)(a.pix0 + t * WT), 0, bar, policy);
+    };
     // Each CTA owns a run of 4 * tiles_per_warp consecutive warp tiles (its warps interleave);
     // the hardware CTA scheduler balances the runs over the SMs (a fully persistent grid with a
     // static tile assignment left SMs idle 17 % of the time: SMs do not all see the same
@@ -367,10 +535,7 @@ stack_meanclip_tmap_kernel(const __grid_constant__ CUtensorMap tmap, const __gri
     const int64_t tile_end = (tile - warp + run < ntiles) ? tile - warp + run : ntiles;
     constexpr int64_t nwarps = TPB / 32;
     uint32_t parity = 0;
-    if (tile < tile_end && lane == 0) {
-        mbar_expect_tx(bar, tile_bytes);
-        tma_load_2d(stage, &tmap, (int32_t)(a.pix0 + tile * WT), 0, bar, policy);
-    }
+    if (tile < tile_end && lane == 0) issue(tile);
     for (; tile < tile_end; tile += nwarps) {
         while (!mbar_try_wait(bar, parity)) {}
         parity ^= 1u;
@@ -384,10 +549,7 @@ stack_meanclip_tmap_kernel(const __grid_constant__ CUtensorMap tmap, const __gri
         // re-arm the stage once the sums (which depend on every staged sample of every lane of
         // this warp instruction stream) exist: the predicate below carries that dependence
         auto rearm = [&](float s2) {
-            if (lane == 0 && next < tile_end && s2 != -1.f) {
-                mbar_expect_tx(bar, tile_bytes);
-                tma_load_2d(stage, &tmap, (int32_t)(a.pix0 + next * WT), 0, bar, policy);
-            }
+            if (lane == 0 && next < tile_end && s2 != -1.f) issue(next);
             __syncwarp();
         };
         meanclip_pixel<NB, NLO, SYM>(y, fp, a, a.pix0 + tile * WT + lane, rearm);

@@ -98,7 +98,7 @@ const char* apgpu_stack_kernel_name(int N, int method, double k_lo, double k_hi,
 
 /* How the last apgpu_stack_reduce_f32 call of the calling thread fed the
  * meanclip kernel: -1 not a meanclip launch, 0 direct global loads, 1 CTA-wide
- * bulk copies, 2 warp-granular cp.async, 3 warp-granular tensor-map TMA.  For
+ * bulk copies, 2 warp-granular cp.async, 3 warp-granular tensor-map TMA, 4 lane-split cp.async (long stacks), 5 warp-cooperative swizzled tensor-map TMA (long stacks).  For
  * tests and the benchmark's bookkeeping (a requested staging falls back to 0
  * when its alignment / layout preconditions do not hold). */
 int apgpu_stack_last_staging(void);

@@ -1,8 +1,8 @@
 import sys, torch
 sys.path.insert(0, '/root/repo')
 from astrophotography_b200 import kernels
-prefer = sys.argv[1]
-n, h, w = 100, 2048, 9576
+prefer = None if sys.argv[1] == "default" else sys.argv[1]
+n, h, w = (int(sys.argv[2]) if len(sys.argv) > 2 else 100), (int(sys.argv[3]) if len(sys.argv) > 3 else 2048), 9576
 g = torch.Generator(device='cuda'); g.manual_seed(1)
 cube = torch.empty((n, h, w), dtype=torch.float32, device='cuda')
 for i in range(n):

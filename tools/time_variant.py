@@ -5,7 +5,7 @@
 import sys, os, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from astrophotography_b200 import kernels
-prefer = sys.argv[1]
+prefer = None if sys.argv[1] == "default" else sys.argv[1]
 n, h, w = (int(x) for x in sys.argv[2:5]) if len(sys.argv) >= 5 else (100, 6388, 9576)
 g = torch.Generator(device='cuda'); g.manual_seed(1)
 cube = torch.empty((n, h, w), dtype=torch.float32, device='cuda')
