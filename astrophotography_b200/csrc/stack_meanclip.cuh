@@ -36,6 +36,27 @@ constexpr int meanclip_min_blocks(int NB) {
 // The per-pixel work, given the N raw samples of pixel p in y[] (padding = 0).
 constexpr int WT = 32;      // pixels per warp tile of the warp-granular staged kernels
 
+__device__ __forceinline__ float fast_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_sqrt(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+template <int J, int NP>
+__device__ __forceinline__ float2 pair_or_zero(const float2 (&y)[NP]) {
+    if constexpr (J < NP) return y[J];
+    else return make_float2(0.f, 0.f);
+}
+template <int J, int NP>
+__device__ __forceinline__ void put_pair(float2 (&y)[NP], const float2 v) {
+    if constexpr (J < NP) y[J] = v;
+}
+
 struct NoHook { __device__ __forceinline__ void operator()(float) const {} };
 
 // P lanes of a warp share one pixel (lane = r * (32/P) + q holds the samples i = P*j + r of pixel q):
@@ -105,7 +126,7 @@ __device__ __forceinline__ void meanclip_pixel(float2 (&y)[NB / 2], const Frames
     constexpr int NP = NB / 2;                         // register pairs
     constexpr int GP = 4;                              // pairs (8 samples) per group
     constexpr int NG = (NP + GP - 1) / GP;
-    static_assert(NG <= 64, "flag word too small");
+    static_assert(NG <= 25, "flag word / rare-pass switch too small");
 
     // Pivot: median of the first three frames (robust to one outlier).  All
     // float32 arithmetic below is on y = x - pivot: sums stay small and the
@@ -171,11 +192,16 @@ __device__ __forceinline__ void meanclip_pixel(float2 (&y)[NB / 2], const Frames
     struct Bounds { float c, t_in, lo_in, hi_in, ylo_out, ylo_in, yhi_in, yhi_out; };
     // returns 0: bounds ready, 1: float64 must decide (degenerate / pivot outside), 2: converged without a pass
     auto make_bounds = [&](Bounds& B) -> int {
-        const float fn = (float)nk;
-        const float c = S1 / fn;
-        const float ex2 = S2 / fn;
+        // Approximate reciprocal / square root (MUFU, <= 2 ulp each) instead of the IEEE sequences: this
+        // scalar block runs once per clip iteration per pixel and the correctly rounded versions cost
+        // ~20 instructions each.  Their few-ulp errors in c and sd are covered by the second term of
+        // the guard band g below; anything degenerate (sd = 0, inf, NaN) fails the g test and
+        // leaves for the float64 routine.
+        const float rn = fast_rcp((float)nk);
+        const float c = S1 * rn;
+        const float ex2 = S2 * rn;
         const float var = ex2 - c * c;
-        const float sd = sqrtf(fmaxf(var, 0.f));
+        const float sd = fast_sqrt(fmaxf(var, 0.f));
         // Bound on |threshold_f32 - threshold_exact| + |y_f32 - y_exact|:
         // group-wise summation (GP + 1 + NG terms deep, + log2 P butterfly steps), unit roundoff
         // doubled for safety; after nsub subtractive updates the summation error is relative to
@@ -183,7 +209,8 @@ __device__ __forceinline__ void meanclip_pixel(float2 (&y)[NB / 2], const Frames
         const float u2 = 1.1920929e-7f;                       // 2^-23
         constexpr int M0 = GP + NG + 9 + (P > 1 ? 4 : 0);
         const float m = (float)M0 + (nsub ? (float)(M0 + 2 * nsub) : 0.f);
-        const float g = m * u2 * (sqrtf(ex2) + 1.5f * kmax * ex2 / sd) + 6.f * u2 * (fabsf(c) + kmax * sd);
+        const float g = 1.0001f * m * u2 * (fast_sqrt(ex2) + 1.5f * kmax * ex2 * fast_rcp(sd)) +
+                        12.f * u2 * (fabsf(c) + kmax * sd);
         if (!(g < 0.25f * kmax * sd)) return 1;               // degenerate (var ~ 0): let float64 decide
         // inner (certainly kept inside) and outer (certainly rejected outside) bounds on t = y - c
         B.c = c;
@@ -225,32 +252,57 @@ __device__ __forceinline__ void meanclip_pixel(float2 (&y)[NB / 2], const Frames
             M_nf = fmaxf(M_nf, flagged ? 0.f : tabs);
         }
     };
-    // rejection pass over the flagged groups, sample by sample: r1, r2 sums over the samples
-    // rejected now, [vmin, vmax] range of the survivors (and zeros) of the flagged groups
+    // Rejection pass over the flagged groups, sample by sample: r1, r2 sums over the samples
+    // rejected now, [vmin, vmax] range of the survivors (and zeros) of the flagged groups.
+    // Each lane walks its own flagged groups (lowest set bit first); the 8 samples of the group
+    // are gathered into scratch registers by a switch on the group index (register arrays need
+    // static indices, so lanes with different groups serialise over ~10 instructions of moves),
+    // the ~70 instructions of per-sample work then run ONCE per round for all lanes together, and a
+    // second switch scatters the survivors back.  (Unrolling the per-sample work into every
+    // group instead made the warp execute it once per distinct flagged group: ~7 times per pass.)
     auto rare_pass = [&](const Bounds& B, const uint64_t flags, float& r1, float& r2, int& nrej_it,
                          float& vmax, float& vmin) {
-#pragma unroll
-        for (int gidx = 0; gidx < NG; ++gidx) {
-            if ((flags >> gidx) & 1) {
-#pragma unroll
-                for (int k = 0; k < 2 * GP; ++k) {
-                    const int i = gidx * 2 * GP + k;
-                    if (i < NB) {
-                        // compare y against bounds shifted by c (not t = y - c: keeps the
-                        // compiler from holding every t of the test pass live in registers)
-                        const float v = (i & 1) ? y[i >> 1].y : y[i >> 1].x;
-                        const bool keep = (v >= B.ylo_out) && (v <= B.yhi_out);
-                        nrej_it += keep ? 0 : 1;                 // certainly rejected
-                        const float vr = keep ? 0.f : v;
-                        const float vk = keep ? v : 0.f;
-                        if (i & 1) y[i >> 1].y = vk; else y[i >> 1].x = vk;
-                        vmax = fmaxf(vmax, vk);
-                        vmin = fminf(vmin, vk);
-                        r1 += vr;
-                        r2 = fmaf(vr, vr, r2);
-                    }
-                }
+        uint32_t f = (uint32_t)flags;
+        while (f) {
+            const int g = __ffs((int)f) - 1;
+            f &= f - 1;
+            float2 t0 = make_float2(0.f, 0.f), t1 = t0, t2 = t0, t3 = t0;
+#define MC_GATHER(G) case G: if constexpr (G < NG) { t0 = pair_or_zero<4 * G, NP>(y); t1 = pair_or_zero<4 * G + 1, NP>(y); \
+                                                     t2 = pair_or_zero<4 * G + 2, NP>(y); t3 = pair_or_zero<4 * G + 3, NP>(y); } break;
+            switch (g) {
+                MC_GATHER(0) MC_GATHER(1) MC_GATHER(2) MC_GATHER(3) MC_GATHER(4) MC_GATHER(5) MC_GATHER(6) MC_GATHER(7)
+                MC_GATHER(8) MC_GATHER(9) MC_GATHER(10) MC_GATHER(11) MC_GATHER(12) MC_GATHER(13) MC_GATHER(14)
+                MC_GATHER(15) MC_GATHER(16) MC_GATHER(17) MC_GATHER(18) MC_GATHER(19) MC_GATHER(20) MC_GATHER(21)
+                MC_GATHER(22) MC_GATHER(23) MC_GATHER(24)
+                default: break;
             }
+#undef MC_GATHER
+            float v[8] = {t0.x, t0.y, t1.x, t1.y, t2.x, t2.y, t3.x, t3.y};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                // compare y against bounds shifted by c (not t = y - c)
+                const bool keep = (v[k] >= B.ylo_out) && (v[k] <= B.yhi_out);
+                nrej_it += keep ? 0 : 1;                         // certainly rejected
+                const float vr = keep ? 0.f : v[k];
+                const float vk = keep ? v[k] : 0.f;
+                v[k] = vk;
+                vmax = fmaxf(vmax, vk);
+                vmin = fminf(vmin, vk);
+                r1 += vr;
+                r2 = fmaf(vr, vr, r2);
+            }
+            t0 = make_float2(v[0], v[1]); t1 = make_float2(v[2], v[3]);
+            t2 = make_float2(v[4], v[5]); t3 = make_float2(v[6], v[7]);
+#define MC_SCATTER(G) case G: if constexpr (G < NG) { put_pair<4 * G, NP>(y, t0); put_pair<4 * G + 1, NP>(y, t1); \
+                                                      put_pair<4 * G + 2, NP>(y, t2); put_pair<4 * G + 3, NP>(y, t3); } break;
+            switch (g) {
+                MC_SCATTER(0) MC_SCATTER(1) MC_SCATTER(2) MC_SCATTER(3) MC_SCATTER(4) MC_SCATTER(5) MC_SCATTER(6) MC_SCATTER(7)
+                MC_SCATTER(8) MC_SCATTER(9) MC_SCATTER(10) MC_SCATTER(11) MC_SCATTER(12) MC_SCATTER(13) MC_SCATTER(14)
+                MC_SCATTER(15) MC_SCATTER(16) MC_SCATTER(17) MC_SCATTER(18) MC_SCATTER(19) MC_SCATTER(20) MC_SCATTER(21)
+                MC_SCATTER(22) MC_SCATTER(23) MC_SCATTER(24)
+                default: break;
+            }
+#undef MC_SCATTER
         }
     };
     // rebuild the sums of the survivors from the registers

@@ -246,7 +246,10 @@ def run_gpu(args, shape):
     mpix = h * w / 1e6
     hbm_peak, peak_src = peaks()
 
-    cube = synth_cube_device(torch, n, h, w, device, seed=1000 + rank)
+    # one equally spaced cube; the variants also time the 200-frame stack of BASELINE config 4
+    n_alloc = n if (args.no_variants or args.small) else max(n, 200)
+    cube_all = synth_cube_device(torch, n_alloc, h, w, device, seed=1000 + rank)
+    cube = cube_all[:n]
     out = {"data": torch.empty((h, w), dtype=torch.float32, device=device),
            "nrej": torch.empty((h, w), dtype=torch.uint8, device=device)}
     torch.cuda.synchronize()
@@ -265,7 +268,9 @@ def run_gpu(args, shape):
     value = world * n * mpix / (ms_per_step * 1e-3)
     alg_bytes = (4 * n + 5) * h * w
     achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
-    kname = kernels.stack_kernel_name(n, **HEADLINE)
+    STAGING = {-1: "", 0: "/direct-loads", 1: "/bulk-copy-cta", 2: "/cp.async-warp", 3: "/tensormap-tma-warp",
+               4: "/lane-split-cp.async", 5: "/warp-coop-swizzled-tensormap-tma"}
+    kname = kernels.stack_kernel_name(n, **HEADLINE) + STAGING.get(kernels.stack_last_staging(), "")
 
     # ---- other kernels of the path (rank 0 reporting only; short runs) ----
     variants = {}
@@ -283,8 +288,8 @@ def run_gpu(args, shape):
         med = dict(method="median", maxiters=0)
         add_variant("stack_median[%s]" % kernels.stack_kernel_name(n, **med),
                     lambda: kernels.stack_reduce(cube, out=out, want_nrej=False, **med), n * mpix, (4 * n + 4) * h * w)
-        add_variant("stack_kappa_sigma_registers[%s]" % kernels.stack_kernel_name(n, prefer="registers", **HEADLINE),
-                    lambda: kernels.stack_reduce(cube, out=out, prefer="registers", **HEADLINE), n * mpix, alg_bytes)
+        add_variant("stack_kappa_sigma_registers_direct_loads[%s]" % kernels.stack_kernel_name(n, prefer="registers", **HEADLINE),
+                    lambda: kernels.stack_reduce(cube, out=out, prefer="registers_direct", **HEADLINE), n * mpix, alg_bytes)
         add_variant("stack_kappa_sigma_registers_cpasync_staged[%s]" % kernels.stack_kernel_name(n, prefer="registers", **HEADLINE),
                     lambda: kernels.stack_reduce(cube, out=out, prefer="registers_cpasync", **HEADLINE), n * mpix, alg_bytes)
         add_variant("stack_kappa_sigma_registers_tensormap_staged[%s]" % kernels.stack_kernel_name(n, prefer="registers", **HEADLINE),
@@ -293,9 +298,14 @@ def run_gpu(args, shape):
                     lambda: kernels.stack_reduce(cube, out=out, prefer="registers_tma", **HEADLINE), n * mpix, alg_bytes)
         add_variant("stack_kappa_sigma_shared[%s]" % kernels.stack_kernel_name(n, prefer="shared", **HEADLINE),
                     lambda: kernels.stack_reduce(cube, out=out, prefer="shared", **HEADLINE), n * mpix, alg_bytes)
-        c30 = cube[:30]
-        add_variant("stack_kappa_sigma_N30[%s]" % kernels.stack_kernel_name(30, **HEADLINE),
-                    lambda: kernels.stack_reduce(c30, out=out, **HEADLINE), 30 * mpix, (4 * 30 + 5) * h * w)
+        for nn in (16, 30, 64, 128, 200):
+            if nn > n_alloc:
+                continue
+            cn = cube_all[:nn]
+            kernels.stack_reduce(cn, out=out, **HEADLINE)
+            tag = kernels.stack_kernel_name(nn, **HEADLINE) + STAGING.get(kernels.stack_last_staging(), "")
+            add_variant("stack_kappa_sigma_N%d[%s]" % (nn, tag),
+                        lambda cn=cn: kernels.stack_reduce(cn, out=out, **HEADLINE), nn * mpix, (4 * nn + 5) * h * w)
         raw = torch.randint(0, 65535, (h, w), dtype=torch.int32, device=device).to(torch.int16).view(torch.uint16)
         bias, dark = cube[0], cube[1]
         flat = (30000.0 * (1 + 0.01 * torch.randn((h, w), device=device))).contiguous()
