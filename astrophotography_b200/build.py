@@ -21,7 +21,7 @@ INCLUDE = os.path.join(ROOT, "include")
 BUILD_DIR = os.path.join(PKG_DIR, "_build")
 LIB_PATH = os.path.join(PKG_DIR, "libapgpu.so")
 
-SOURCES = ["stack_meanclip_coop_p8.cu", "stack_meanclip_coop_p4.cu", "stack_meanclip_coop_p2.cu", "stack_meanclip_split_p4.cu", "stack_meanclip_split_p2.cu", "stack_meanclip_split_p8.cu", "stack_meanclip_mid.cu", "stack_meanclip_hi.cu", "stack_meanclip_lo.cu", "stack_sorted_medmad1.cu",
+SOURCES = ["stack_meanclip_coop_p8.cu", "stack_meanclip_coop_p4.cu", "stack_meanclip_coop_p2.cu", "stack_meanclip_split_p8.cu", "stack_meanclip_mid.cu", "stack_meanclip_hi.cu", "stack_meanclip_lo.cu", "stack_sorted_medmad1.cu",
            "stack_sorted_med.cu", "stack_meanclip_smem.cu", "stack_generic.cu", "stack.cu",
            "apgpu_core.cu", "calibrate.cu", "badpix.cu", "stats.cu"]
 NVCC_FLAGS = [

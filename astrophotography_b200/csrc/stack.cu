@@ -92,11 +92,11 @@ int stack_dispatch_meanclip_split(const float* const* frames, const StackArgs& a
                  APGPU_STACK_PREFER_REGISTERS))
         return APGPU_ERR_UNSUPPORTED;
     if (!stack_is_cube(frames, a.N, a.pix0 + a.npix)) return APGPU_ERR_UNSUPPORTED;
-    static const bool no_coop = getenv("APGPU_NO_COOP") != nullptr;           // dev tuning
+    static const bool no_coop = getenv("APGPU_NO_COOP") != nullptr;           // tuning knob
     if (!no_coop && a.N <= 512) {
         // lanes per pixel (measured, tools/time_variant.py): short per-lane arrays (<= 64 samples) keep the
         // unrolled code and the register count small, which matters more than the extra shuffle steps
-        static const int force_p = getenv("APGPU_COOP_P") ? atoi(getenv("APGPU_COOP_P")) : 0;   // dev tuning
+        static const int force_p = getenv("APGPU_COOP_P") ? atoi(getenv("APGPU_COOP_P")) : 0;   // tuning knob
         int P = a.N <= 128 ? 2 : (a.N <= 256 ? 4 : 8);
         if (force_p) P = force_p;
         int rc = APGPU_ERR_UNSUPPORTED;
@@ -105,9 +105,8 @@ int stack_dispatch_meanclip_split(const float* const* frames, const StackArgs& a
         if (P == 8) rc = stack_dispatch_meanclip_coop_p8(frames, a, st, done_pix);
         if (rc != APGPU_ERR_UNSUPPORTED) return rc;
     }
-    if (a.N <= 200) return stack_dispatch_meanclip_split_p2(frames, a, st, done_pix);
-    if (a.N <= 512) return stack_dispatch_meanclip_split_p4(frames, a, st, done_pix);
-    return stack_dispatch_meanclip_split_p8(frames, a, st, done_pix);
+    if (a.N > 512) return stack_dispatch_meanclip_split_p8(frames, a, st, done_pix);
+    return APGPU_ERR_UNSUPPORTED;
 }
 
 int stack_dispatch_meanclip(int nb, const float* const* frames, const StackArgs& a, cudaStream_t st, int flags) {
@@ -231,8 +230,7 @@ extern "C" int apgpu_stack_reduce_f32(const float* const* frames, int N, int64_t
 
     // long stacks on equally spaced frames: the lane-split tensor-map kernels take every full warp tile,
     // whatever follows only sees the (< 32-pixel) tail
-    static const bool split_100 = getenv("APGPU_SPLIT_100") != nullptr;         // dev tuning
-    if (N > (split_100 ? 80 : 100) && meanclip_eligible(N, method, k_lo, k_hi, maxiters, cen, dev, flags)) {
+    if (N > 100 && meanclip_eligible(N, method, k_lo, k_hi, maxiters, cen, dev, flags)) {
         int64_t done = 0;
         const int rc = stack_dispatch_meanclip_split(frames, a, st, flags, &done);
         if (rc != APGPU_OK && rc != APGPU_ERR_UNSUPPORTED) return rc;

@@ -278,12 +278,11 @@ int stack_dispatch_meanclip_lo(int nb, const float* const* frames, const StackAr
 int stack_dispatch_meanclip_mid(int nb, const float* const* frames, const StackArgs& a, cudaStream_t st, int flags);
 int stack_dispatch_meanclip_hi(int nb, const float* const* frames, const StackArgs& a, cudaStream_t st, int flags);
 int stack_launch_meanclip_smem(const float* const* frames, const StackArgs& a, cudaStream_t st);
-// lane-split tensor-map kernels (N > 100 on equally spaced frames): returns APGPU_ERR_UNSUPPORTED when there
+// long stacks (N > 100) on equally spaced frames -- warp-cooperative kernels up to N = 512, lane-split
+// cp.async kernels beyond: returns APGPU_ERR_UNSUPPORTED when there
 // is no bucket; *done_pix = pixels (from a.pix0) that were reduced, the caller finishes the tail
 int stack_dispatch_meanclip_split(const float* const* frames, const StackArgs& a, cudaStream_t st, int flags,
                                   int64_t* done_pix);
-int stack_dispatch_meanclip_split_p2(const float* const* frames, const StackArgs& a, cudaStream_t st, int64_t* done_pix);
-int stack_dispatch_meanclip_split_p4(const float* const* frames, const StackArgs& a, cudaStream_t st, int64_t* done_pix);
 int stack_dispatch_meanclip_split_p8(const float* const* frames, const StackArgs& a, cudaStream_t st, int64_t* done_pix);
 int stack_dispatch_meanclip_coop_p2(const float* const* frames, const StackArgs& a, cudaStream_t st, int64_t* done_pix);
 int stack_dispatch_meanclip_coop_p4(const float* const* frames, const StackArgs& a, cudaStream_t st, int64_t* done_pix);

@@ -1,5 +1,6 @@
-// Frame-stack reducer: lane-split kappa-sigma kernels for long stacks (100 < N <= 1024) on equally
-// spaced frames.  See stack_common.cuh / stack_meanclip.cuh.
+// Frame-stack reducer: lane-split kappa-sigma kernels for very long stacks (512 < N <= 1024) on equally
+// spaced frames (shorter stacks use the warp-cooperative kernels of stack_meanclip_coop.cuh, which keep
+// 128-byte rows and are 2-3x faster; this simpler variant covers what they do not).  See stack_common.cuh / stack_meanclip.cuh.
 //
 // The register-resident meanclip kernel keeps all N samples of a pixel in one thread, which stops
 // scaling at N ~ 100 (128 registers, 4 warps per scheduler; at N = 200 it needs 255 registers and
