@@ -47,7 +47,7 @@ const Bucket MEANCLIP_BUCKETS[] = {{8, 2}, {16, 8}, {24, 16}, {32, 24}, {48, 32}
                                    {100, 80}, {128, 100}, {160, 128}, {200, 160}};
 const Bucket SORT_BUCKETS[] = {{4, 0}, {8, 4}, {12, 8}, {16, 12}, {20, 16}, {24, 20}, {32, 24}, {40, 32},
                                {48, 40}, {56, 48}, {64, 56}, {72, 64}, {80, 72}, {90, 80}, {100, 90},
-                               {112, 100}, {128, 112}};
+                               {112, 100}, {128, 112}, {160, 128}, {200, 160}};
 
 template <size_t K>
 const Bucket* find_bucket(const Bucket (&b)[K], int N) {

@@ -747,7 +747,8 @@ int launch_meanclip(const float* const* frames, const StackArgs& a_in, cudaStrea
     if (flags & APGPU_STACK_DIRECT_LOADS) staging = 0;
     if (flags & APGPU_STACK_USE_CPASYNC) staging = 2;
     if (flags & APGPU_STACK_USE_TENSORMAP) staging = 3;
-    if (staging == 3 && !stack_is_cube(frames, a.N, a.pix0 + a.npix))
+    // (a TMA box must start on a 16-byte boundary: found by tests/test_gpu_stack.py::test_meanclip_row_band_on_cube)
+    if (staging == 3 && (!stack_is_cube(frames, a.N, a.pix0 + a.npix) || a.pix0 % 4 != 0))
         staging = (flags & APGPU_STACK_USE_TENSORMAP) ? 0 : (NB <= 64 ? 2 : 0);
     // the per-warp stages must leave room for meanclip_min_blocks CTAs per SM
     const size_t smem_cta = (size_t)NB * sizeof(float*) + (size_t)(TPB / 32) * NB * WT * sizeof(float);

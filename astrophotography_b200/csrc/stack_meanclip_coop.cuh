@@ -111,6 +111,7 @@ int launch_meanclip_coop_sym(const float* const* frames, const StackArgs& a_in, 
     const int64_t ntiles = a.npix / 32;
     *done_pix = 0;
     if (ntiles == 0) return APGPU_OK;
+    if (a.pix0 % 4 != 0) return APGPU_ERR_UNSUPPORTED;        // a TMA box must start on a 16-byte boundary
     // One tile = the fewest TMA boxes (<= 256 rows each, whole 8-row swizzle atoms) on one mbarrier;
     // smaller boxes were measured (APGPU_COOP_BOX_ROWS): no gain.
     a.box_rows = 8;

@@ -25,7 +25,7 @@ template <int NB> __device__ __forceinline__ void sort_regs(float (&x)[NB]);
 APGPU_DEF_SORT(4) APGPU_DEF_SORT(8) APGPU_DEF_SORT(12) APGPU_DEF_SORT(16) APGPU_DEF_SORT(20)
 APGPU_DEF_SORT(24) APGPU_DEF_SORT(32) APGPU_DEF_SORT(40) APGPU_DEF_SORT(48) APGPU_DEF_SORT(56)
 APGPU_DEF_SORT(64) APGPU_DEF_SORT(72) APGPU_DEF_SORT(80) APGPU_DEF_SORT(90) APGPU_DEF_SORT(100)
-APGPU_DEF_SORT(112) APGPU_DEF_SORT(128)
+APGPU_DEF_SORT(112) APGPU_DEF_SORT(128) APGPU_DEF_SORT(160) APGPU_DEF_SORT(200)
 
 template <int NB, int NLO, int MODE>
 __global__ void __launch_bounds__(STPB, (NB <= 32 ? 4 : (NB <= 100 ? 2 : 1)))
@@ -163,6 +163,7 @@ int dispatch_sorted(int nb, const float* const* frames, const StackArgs& a, cuda
     SO_CASE(4, 0) SO_CASE(8, 4) SO_CASE(12, 8) SO_CASE(16, 12) SO_CASE(20, 16) SO_CASE(24, 20)
     SO_CASE(32, 24) SO_CASE(40, 32) SO_CASE(48, 40) SO_CASE(56, 48) SO_CASE(64, 56) SO_CASE(72, 64)
     SO_CASE(80, 72) SO_CASE(90, 80) SO_CASE(100, 90) SO_CASE(112, 100) SO_CASE(128, 112)
+    SO_CASE(160, 128) SO_CASE(200, 160)
     return APGPU_ERR_UNSUPPORTED;
 }
 

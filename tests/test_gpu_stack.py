@@ -132,7 +132,7 @@ FAST_CASES = [
 ]
 
 
-@pytest.mark.parametrize("n", [3, 4, 5, 8, 9, 16, 17, 24, 30, 33, 50, 64, 65, 81, 90, 99, 100, 101, 113, 128])
+@pytest.mark.parametrize("n", [3, 4, 5, 8, 9, 16, 17, 24, 30, 33, 50, 64, 65, 81, 90, 99, 100, 101, 113, 128, 129, 160, 161, 200])
 @pytest.mark.parametrize("case", FAST_CASES, ids=lambda c: "-".join(map(str, c)))
 @pytest.mark.parametrize("quantise", [False, True])
 def test_fast_kernels_match_oracle(cuda, n, case, quantise):
@@ -221,6 +221,55 @@ def test_meanclip_lane_split_long_stacks(cuda, n, case):
         assert np.array_equal(got["allmasked"], exp["allmasked"])
         _assert_close_data(got["data"].astype(np.float64), exp["data"], RTOL32 if not out_f64 else 2e-7, 12.0)
         _assert_close_data(got["uncert"].astype(np.float64), exp["uncert"], 1e-5, 1e-3)
+
+
+@pytest.mark.parametrize("n", [30, 100, 150, 300, 600])
+def test_meanclip_separately_allocated_frames(cuda, n):
+    """N frame pointers that are NOT equally spaced (the C ABI allows it): no tensor map can describe them,
+    the dispatcher must fall back to the pointer-table kernels and still match the oracle."""
+    torch = cuda
+    from astrophotography_b200 import kernels
+    st = _stack(n, (9, 70), seed=60 + n)
+    exp = _oracle(st, "average", 3.0, 3.0, 5, "mean", "std")
+    frames, pad = [], []
+    for i in range(n):
+        frames.append(torch.from_numpy(np.ascontiguousarray(st[i])).cuda())
+        pad.append(torch.empty(640 * (1 + i % 3), device="cuda"))            # unequal gaps between the frames
+    gaps = {frames[i + 1].data_ptr() - frames[i].data_ptr() for i in range(n - 1)}
+    assert len(gaps) > 1
+    res = kernels.stack_reduce(frames, method="average", k_lo=3.0, k_hi=3.0, maxiters=5, cen="mean", dev="std",
+                               want_nrej=True, want_allmasked=True)
+    torch.cuda.synchronize()
+    assert kernels.stack_last_staging() in (-1, 0, 2)
+    assert np.array_equal(res["nrej"].cpu().numpy().astype(np.int64), exp["nrej"])
+    _assert_close_data(res["data"].cpu().numpy().astype(np.float64), exp["data"], RTOL32, 12.0)
+    del pad
+
+
+@pytest.mark.parametrize("n,shape,row0,nrows", [(100, (8, 75), 3, 4), (64, (16, 76), 5, 9), (200, (8, 75), 1, 6),
+                                                (300, (12, 68), 2, 9)])
+def test_meanclip_row_band_on_cube(cuda, n, shape, row0, nrows):
+    """Row bands of a cube (multi-GPU sharding): the band may start at a pixel that is not 16-byte aligned
+    (a TMA box must start on one: the dispatcher then falls back to the pointer-table kernels, which this test
+    found out the hard way); rows outside the band are left untouched."""
+    torch = cuda
+    from astrophotography_b200 import kernels
+    st = _stack(n, shape, seed=70 + n)
+    exp = _oracle(st, "average", 3.0, 3.0, 5, "mean", "std")
+    cube = torch.from_numpy(st).cuda()
+    out = {"data": torch.full(shape, -7.0, dtype=torch.float32, device="cuda"),
+           "nrej": torch.full(shape, 255, dtype=torch.uint8 if n <= 255 else torch.uint16, device="cuda")}
+    kernels.stack_reduce(cube, method="average", k_lo=3.0, k_hi=3.0, maxiters=5, cen="mean", dev="std",
+                         row0=row0, nrows=nrows, out=out)
+    torch.cuda.synchronize()
+    aligned = (row0 * shape[1]) % 4 == 0
+    assert (kernels.stack_last_staging() in (3, 5)) == aligned
+    data, nrej = out["data"].cpu().numpy(), out["nrej"].cpu().numpy()
+    band = slice(row0, row0 + nrows)
+    assert np.array_equal(nrej[band].astype(np.int64), exp["nrej"][band])
+    _assert_close_data(data[band].astype(np.float64), exp["data"][band], RTOL32, 12.0)
+    keep = np.ones(shape[0], bool); keep[band] = False
+    assert (data[keep] == -7.0).all() and (nrej[keep] == 255).all()
 
 
 def test_fast_uncert(cuda):
