@@ -306,6 +306,29 @@ def run_gpu(args, shape):
             tag = kernels.stack_kernel_name(nn, **HEADLINE) + STAGING.get(kernels.stack_last_staging(), "")
             add_variant("stack_kappa_sigma_N%d[%s]" % (nn, tag),
                         lambda cn=cn: kernels.stack_reduce(cn, out=out, **HEADLINE), nn * mpix, (4 * nn + 5) * h * w)
+        # BASELINE config 2 end to end on the device: master bias + dark + flat (30 frames of 4096x4096 each, the
+        # reference's ApMasterCal setting: 5-sigma median/MAD clip, one pass, mean), flat normalisation, then
+        # calibration and bad-pixel repair of one uint16 science frame
+        if h >= 4096 and w >= 4096:
+            h2 = w2 = 4096
+            c2 = cube_all[:90].reshape(-1)[: 90 * h2 * w2].view(90, h2, w2)
+            raw2 = torch.randint(0, 65535, (h2, w2), dtype=torch.int32, device=device).to(torch.int16).view(torch.uint16)
+            mask2 = torch.from_numpy(synth.badpix_mask((h2, w2), auto_fraction=1e-3)).to(device)
+            m_out = [{"data": torch.empty((h2, w2), dtype=torch.float32, device=device),
+                      "nrej": torch.empty((h2, w2), dtype=torch.uint8, device=device)} for _ in range(3)]
+            cal2 = torch.empty((h2, w2), dtype=torch.float32, device=device)
+
+            def config2():
+                for k in range(3):
+                    kernels.stack_reduce(c2[30 * k: 30 * k + 30], out=m_out[k], **ref)
+                nflat2, _ = kernels.flat_normalise(m_out[2]["data"])
+                kernels.calibrate(raw2, m_out[0]["data"], m_out[1]["data"], nflat2, 1.0 / 3.0, True, out=cal2)
+                kernels.fix_badpix(cal2, mask2, 2)
+
+            px2 = h2 * w2
+            add_variant("config2_masters_3x30x4096x4096_medmad_then_calibrate_repair[%s]" % kernels.stack_kernel_name(30, **ref),
+                        config2, 90 * px2 / 1e6, (3 * (4 * 30 + 5) + 8 + 18 + 9) * px2)
+            del c2, raw2, mask2, m_out, cal2
         raw = torch.randint(0, 65535, (h, w), dtype=torch.int32, device=device).to(torch.int16).view(torch.uint16)
         bias, dark = cube[0], cube[1]
         flat = (30000.0 * (1 + 0.01 * torch.randn((h, w), device=device))).contiguous()

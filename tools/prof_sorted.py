@@ -1,7 +1,7 @@
 import sys, torch
 sys.path.insert(0, '/root/repo')
 from astrophotography_b200 import kernels
-n, h, w = 100, 1024, 9576
+n, h, w = (int(sys.argv[1]) if len(sys.argv) > 1 else 100), 2048, 9576
 g = torch.Generator(device='cuda'); g.manual_seed(1)
 cube = torch.empty((n, h, w), dtype=torch.float32, device='cuda')
 for i in range(n):
