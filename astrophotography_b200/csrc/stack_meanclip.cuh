@@ -570,22 +570,23 @@ stack_meanclip_tmap_kernel(const __grid_constant__ CUtensorMap tmap, const __gri
     if (lane == 0) mbar_init(bar, 1);
     for (int i = N * WT + lane; i < NB * WT; i += 32) stage[i] = 0.f;         // padding rows: never copied into
     __syncwarp();
-    const uint64_t policy = l2_evict_first_policy();
     // one box = the whole tile (cutting it into several concurrent boxes was measured: no gain)
-    const uint32_t tile_bytes = (uint32_t)N * WT * sizeof(float);
-    auto issue = [&](int64_t t) {
-        mbar_expect_tx(bar, tile_bytes);
-        tma_load_2d(stage, &tmap, (int32_t)(a.pix0 + t * WT), 0, bar, policy);
+    // (all pixel / tile indices fit 32 bits: the host only takes this path below 2^31 pixels; 64-bit
+    // loop state cost spilled registers and a local-memory reload at the end of every tile)
+    const int pix0 = (int)a.pix0;
+    auto issue = [&](int t) {                       // (policy / byte count rebuilt here: not worth live registers)
+        mbar_expect_tx(bar, (uint32_t)a.N * WT * sizeof(float));
+        tma_load_2d(stage, &tmap, pix0 + t * WT, 0, bar, l2_evict_first_policy());
     };
     // Each CTA owns a run of 4 * tiles_per_warp consecutive warp tiles (its warps interleave);
     // the hardware CTA scheduler balances the runs over the SMs (a fully persistent grid with a
     // static tile assignment left SMs idle 17 % of the time: SMs do not all see the same
     // memory throughput).
-    const int64_t ntiles = a.npix / WT;                                       // full warp tiles (host launches the tail)
-    const int64_t run = (int64_t)(TPB / 32) * a.tiles_per_warp;
-    int64_t tile = (int64_t)blockIdx.x * run + warp;
-    const int64_t tile_end = (tile - warp + run < ntiles) ? tile - warp + run : ntiles;
-    constexpr int64_t nwarps = TPB / 32;
+    const int ntiles = (int)(a.npix / WT);                                    // full warp tiles (host launches the tail)
+    const int run = (TPB / 32) * a.tiles_per_warp;
+    int tile = (int)blockIdx.x * run + warp;
+    const int tile_end = min((int)(blockIdx.x + 1) * run, ntiles);
+    constexpr int nwarps = TPB / 32;
     uint32_t parity = 0;
     if (tile < tile_end && lane == 0) issue(tile);
     for (; tile < tile_end; tile += nwarps) {
@@ -597,14 +598,14 @@ stack_meanclip_tmap_kernel(const __grid_constant__ CUtensorMap tmap, const __gri
             y[j].x = stage[(2 * j) * WT + lane];
             y[j].y = stage[(2 * j + 1) * WT + lane];
         }
-        const int64_t next = tile + nwarps;
+        const int next = tile + nwarps;
         // re-arm the stage once the sums (which depend on every staged sample of every lane of
         // this warp instruction stream) exist: the predicate below carries that dependence
         auto rearm = [&](float s2) {
             if (lane == 0 && next < tile_end && s2 != -1.f) issue(next);
             __syncwarp();
         };
-        meanclip_pixel<NB, NLO, SYM>(y, fp, a, a.pix0 + tile * WT + lane, rearm);
+        meanclip_pixel<NB, NLO, SYM>(y, fp, a, (int64_t)(uint32_t)(pix0 + tile * WT + lane), rearm);
     }
 }
 
