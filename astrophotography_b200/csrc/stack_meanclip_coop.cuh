@@ -57,18 +57,20 @@ stack_meanclip_coop_kernel(const __grid_constant__ CUtensorMap tmap, const __gri
         const int row8 = RB * r + jl;
         lane_base[jl] = reinterpret_cast<const float*>(stage + row8 * 128 + ((c ^ row8) & 7) * 16 + cw * 4);
     }
-    const uint64_t policy = l2_evict_first_policy();
-    const int box_rows = a.box_rows, nchunks = a.nchunks;
-    const uint32_t tile_bytes = (uint32_t)NB * 128;     // out-of-bounds rows (frames >= N) are zero-filled and count
-    const int64_t ntiles = a.npix / 32;                 // full tiles (the host finishes the tail)
-    const int64_t run = (int64_t)G * a.tiles_per_warp;
-    int64_t tile = (int64_t)blockIdx.x * run + grp;
-    const int64_t tile_end = ((int64_t)(blockIdx.x + 1) * run < ntiles) ? (int64_t)(blockIdx.x + 1) * run : ntiles;
+    // (all pixel / tile indices fit 32 bits: the host only takes this path below 2^31 pixels)
+    const int pix0 = (int)a.pix0;
+    const int ntiles = (int)(a.npix / 32);              // full tiles (the host finishes the tail)
+    const int run = G * a.tiles_per_warp;
+    int tile = (int)blockIdx.x * run + grp;
+    const int tile_end = min((int)(blockIdx.x + 1) * run, ntiles);
     uint32_t parity = 0;
-    auto issue = [&](int64_t t) {
-        mbar_expect_tx(full, tile_bytes);
-        for (int k = 0; k < nchunks; ++k)
-            tma_load_2d(stage + (size_t)k * box_rows * 128, &tmap, (int32_t)(a.pix0 + t * 32), k * box_rows, full, policy);
+    auto issue = [&](int t) {
+        // out-of-bounds rows (frames >= N) are zero-filled and count towards the mbarrier's byte total
+        mbar_expect_tx(full, (uint32_t)NB * 128);
+        const uint64_t policy = l2_evict_first_policy();
+        const int box_rows = a.box_rows;
+        for (int k = 0; k < a.nchunks; ++k)
+            tma_load_2d(stage + (size_t)k * box_rows * 128, &tmap, pix0 + t * 32, k * box_rows, full, policy);
     };
     if (tile < tile_end && wi == 0 && lane == 0) issue(tile);
     for (; tile < tile_end; tile += G) {
@@ -83,7 +85,7 @@ stack_meanclip_coop_kernel(const __grid_constant__ CUtensorMap tmap, const __gri
         // pivot of the pixel: median of its first three frames (rows 0, 1, 2 of column col)
         const float* s0 = reinterpret_cast<const float*>(stage + cw * 4);
         const float pivot = med3(s0[(c ^ 0) * 4], s0[32 + (c ^ 1) * 4], s0[64 + (c ^ 2) * 4]);
-        const int64_t next = tile + G;
+        const int next = tile + G;
         // the last warp of the group to have consumed its samples re-arms the stage (the sums depend on
         // every staged sample of this warp's instruction stream: the predicate carries that dependence)
         auto rearm = [&](float s2) {
@@ -99,7 +101,7 @@ stack_meanclip_coop_kernel(const __grid_constant__ CUtensorMap tmap, const __gri
             __syncwarp();
         };
         meanclip_pixel<NBL, NLO, SYM, decltype(rearm), P, CubeFrames, SwizzledFrames<P>>(
-            y, cube, a, a.pix0 + tile * 32 + col, rearm, pivot, 0xffffffffu, r);
+            y, cube, a, (int64_t)(uint32_t)(pix0 + tile * 32 + col), rearm, pivot, 0xffffffffu, r);
     }
 }
 
