@@ -25,7 +25,7 @@ namespace apgpu_stack {
 __host__ __device__ constexpr int coop_tpb(int P) { return 32 * (P > 4 ? P : 4); }
 // CTAs per SM: shorter per-lane sample arrays need fewer registers, so more warps stay resident
 __host__ __device__ constexpr int coop_min_blocks(int NBL, int P) {
-    return (NBL <= 40 ? 6 : (NBL <= 50 ? 5 : (NBL <= 100 ? 4 : 3))) * 128 / coop_tpb(P);
+    return P == 8 ? (NBL <= 50 ? 3 : 2) : (NBL <= 40 ? 6 : (NBL <= 50 ? 5 : (NBL <= 100 ? 4 : 3))) * 128 / coop_tpb(P);
 }
 
 template <int NBL, int NLO, int P, bool SYM>
