@@ -649,11 +649,15 @@ stack_meanclip_cpasync_kernel(const __grid_constant__ FramePtrs<NB> fp, const __
     for (int i = threadIdx.x; i < N; i += TPB) ptab[i] = fp.p[i];
     for (int i = N * WT + lane; i < NB * WT; i += 32) stage[i] = 0.f;         // padding rows: never copied into
     __syncthreads();
+    // CTA runs of 4 * tiles_per_warp consecutive warp tiles, balanced by the hardware CTA scheduler
+    // (see the tensor-map kernel: a static persistent assignment left SMs idle)
     const int64_t ntiles = a.npix / WT;                                       // full warp tiles (host launches the tail)
-    const int64_t nwarps = (int64_t)gridDim.x * (TPB / 32);
-    int64_t tile = (int64_t)blockIdx.x * (TPB / 32) + warp;
-    if (tile < ntiles) issue_warp_tile(ptab, N, a.pix0 + tile * WT, stage, lane);
-    for (; tile < ntiles; tile += nwarps) {
+    const int64_t run = (int64_t)(TPB / 32) * a.tiles_per_warp;
+    int64_t tile = (int64_t)blockIdx.x * run + warp;
+    const int64_t tile_end = ((int64_t)(blockIdx.x + 1) * run < ntiles) ? (int64_t)(blockIdx.x + 1) * run : ntiles;
+    constexpr int64_t nwarps = TPB / 32;
+    if (tile < tile_end) issue_warp_tile(ptab, N, a.pix0 + tile * WT, stage, lane);
+    for (; tile < tile_end; tile += nwarps) {
         cp_async_wait_all();
         __syncwarp();                                                         // every lane's copies are visible
         float2 y[NB / 2];
@@ -662,10 +666,13 @@ stack_meanclip_cpasync_kernel(const __grid_constant__ FramePtrs<NB> fp, const __
             y[j].x = stage[(2 * j) * WT + lane];
             y[j].y = stage[(2 * j + 1) * WT + lane];
         }
-        __syncwarp();                                                         // stage drained by every lane
         const int64_t next = tile + nwarps;
-        if (next < ntiles) issue_warp_tile(ptab, N, a.pix0 + next * WT, stage, lane);
-        meanclip_pixel<NB, NLO, SYM>(y, fp, a, a.pix0 + tile * WT + lane);
+        // re-arm the stage once every staged sample has been consumed (the sums exist)
+        auto rearm = [&](float s2) {
+            __syncwarp();
+            if (next < tile_end && s2 != -1.f) issue_warp_tile(ptab, N, a.pix0 + next * WT, stage, lane);
+        };
+        meanclip_pixel<NB, NLO, SYM>(y, fp, a, a.pix0 + tile * WT + lane, rearm);
     }
 }
 
@@ -700,10 +707,11 @@ int launch_meanclip_sym(const FramePtrs<NB>& fp, const StackArgs& a, int staging
             const size_t smem = (size_t)NB * sizeof(float*) + (size_t)(TPB / 32) * NB * WT * sizeof(float);
             APGPU_CUDA(cudaFuncSetAttribute(stack_meanclip_cpasync_kernel<NB, NLO, SYM>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int64_t grid = (int64_t)APGPU_NUM_SMS * meanclip_min_blocks(NB);
-            const int64_t need = (ntiles + TPB / 32 - 1) / (TPB / 32);
-            if (grid > need) grid = need;
-            stack_meanclip_cpasync_kernel<NB, NLO, SYM><<<(unsigned)grid, TPB, smem, st>>>(fp, a);
+            StackArgs ac = a;
+            ac.tiles_per_warp = stack_tmap_tiles_per_warp();
+            const int64_t run = (int64_t)(TPB / 32) * ac.tiles_per_warp;
+            const int64_t grid = (ntiles + run - 1) / run;
+            stack_meanclip_cpasync_kernel<NB, NLO, SYM><<<(unsigned)grid, TPB, smem, st>>>(fp, ac);
             APGPU_LAUNCH_CHECK("stack_meanclip_cpasync_kernel");
         }
         rest.pix0 = a.pix0 + ntiles * WT;            // the < 32-pixel tail goes through the direct kernel
@@ -742,7 +750,7 @@ int launch_meanclip(const float* const* frames, const StackArgs& a_in, cudaStrea
     for (int i = NLO; i < NB; ++i) a.tailmask[i - NLO] = i < a.N ? 1.f : 0.f;
     // staging: 0 direct loads, 1 CTA-wide bulk copies, 2 warp-granular cp.async, 3 warp-granular tensor-map TMA.
     // Default (measured, bench.py variants / tools/time_variant.py): the tensor-map TMA pipeline wherever the
-    // frames are equally spaced; otherwise cp.async for the shorter stacks and direct loads from N~80 up.
+    // frames are equally spaced; otherwise cp.async for the medium stacks (85 % at N=64) and direct loads else.
     int staging = 3;
     if (flags & APGPU_STACK_USE_TMA) staging = 1;
     if (flags & APGPU_STACK_DIRECT_LOADS) staging = 0;
@@ -750,7 +758,7 @@ int launch_meanclip(const float* const* frames, const StackArgs& a_in, cudaStrea
     if (flags & APGPU_STACK_USE_TENSORMAP) staging = 3;
     // (a TMA box must start on a 16-byte boundary: found by tests/test_gpu_stack.py::test_meanclip_row_band_on_cube)
     if (staging == 3 && (!stack_is_cube(frames, a.N, a.pix0 + a.npix) || a.pix0 % 4 != 0))
-        staging = (flags & APGPU_STACK_USE_TENSORMAP) ? 0 : (NB <= 64 ? 2 : 0);
+        staging = (flags & APGPU_STACK_USE_TENSORMAP) ? 0 : ((NB > 32 && NB <= 80) ? 2 : 0);   // measured (time_variant.py)
     // the per-warp stages must leave room for meanclip_min_blocks CTAs per SM
     const size_t smem_cta = (size_t)NB * sizeof(float*) + (size_t)(TPB / 32) * NB * WT * sizeof(float);
     if ((staging == 2 || staging == 3) && smem_cta * meanclip_min_blocks(NB) > (size_t)SMEM_MAX_BYTES) staging = 0;
