@@ -47,20 +47,20 @@ stack_sorted_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_const
     float x[NB];
     float z = 0.f;
     double sum_all = 0.0;
+    // Padding slots (i >= N, only possible for i >= NLO) are loaded like real ones -- the host points them at
+    // frame 0 -- and replaced afterwards by uniform selects: no predicated loads / address arithmetic.
+#pragma unroll
+    for (int i = 0; i < NB; ++i) x[i] = ld_stream(fp.p[i] + p32);
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
-        if (APGPU_ACTIVE(i)) {
-            x[i] = ld_stream(fp.p[i] + p32);
-        } else {
-            x[i] = (i - N < nneg) ? -INFINITY : INFINITY;
+        float xa = x[i];
+        if (i >= NLO) {
+            const bool active = i < N;
+            xa = active ? xa : -0.f;                                           // x + (-0) == x bit for bit
+            x[i] = active ? x[i] : ((i - N < nneg) ? -INFINITY : INFINITY);
         }
-    }
-#pragma unroll
-    for (int i = 0; i < NB; ++i) {
-        if (APGPU_ACTIVE(i)) {
-            z = fmaf(x[i], 0.f, z);
-            if (MODE == MODE_MEDMAD1) sum_all = __dadd_rn(sum_all, (double)x[i]);   // frame order, as nanmean
-        }
+        z = fmaf(xa, 0.f, z);
+        if (MODE == MODE_MEDMAD1) sum_all = __dadd_rn(sum_all, (double)xa);     // frame order, as nanmean
     }
     const bool nonfinite = (z != z);          // handled after the (barrier-carrying) sort
 
@@ -145,7 +145,7 @@ stack_sorted_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_const
 template <int NB, int NLO, int MODE>
 int launch_sorted(const float* const* frames, const StackArgs& a, cudaStream_t st) {
     FramePtrs<NB> fp;
-    for (int i = 0; i < NB; ++i) fp.p[i] = i < a.N ? frames[i] : nullptr;
+    for (int i = 0; i < NB; ++i) fp.p[i] = i < a.N ? frames[i] : frames[0];   // padding: loaded, then replaced
     int64_t blocks = (a.npix + STPB - 1) / STPB;
     size_t smem = (MODE == MODE_MEDMAD1) ? (size_t)(NB + 2) * STPB * sizeof(float) : 0;
     if (smem > 48 * 1024)
