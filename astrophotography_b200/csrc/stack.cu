@@ -225,6 +225,7 @@ extern "C" int apgpu_stack_reduce_f32(const float* const* frames, int N, int64_t
     a.out = out_data; a.out_f64 = out_is_f64;
     a.nrej = out_nrej; a.nrej_u16 = nrej_is_u16;
     a.uncert = out_uncert; a.allmasked = out_allmasked;
+    a.one = 1; a.minus_one = -1; a.tiles_per_warp = 0; a.box_rows = 0; a.nchunks = 0;
     cudaStream_t st = (cudaStream_t)stream;
     g_last_staging = -1;
 

@@ -58,6 +58,7 @@ struct StackArgs {
     float tailmask[MEANCLIP_MAX_TAIL];
     int tiles_per_warp;          // tensor-map staged kernels: warp tiles per warp (per group) per CTA
     int box_rows, nchunks;       // warp-cooperative kernel: rows per TMA box, boxes per tile
+    int one, minus_one;          // +1 / -1 as run-time values (sorted kernels: IMAD on the FMA pipe)
 };
 
 template <int CAP> struct FramePtrs {

@@ -1,5 +1,6 @@
 // Frame-stack reducer: sorted<NB, NLO, MODE> register-resident Batcher-network kernels.  See stack_common.cuh.
 #pragma once
+#include <stdlib.h>
 #include "stack_common.cuh"
 #include "sort_networks.inc"
 
@@ -13,21 +14,36 @@ constexpr int MODE_MED = 0;       // method=median, no clipping
 constexpr int MODE_MEDMAD1 = 1;   // one median/MAD clip pass, then the mean (ApMasterCal)
 
 #define CE_X(i, j) { float lo_ = fminf(x[i], x[j]); float hi_ = fmaxf(x[i], x[j]); x[i] = lo_; x[j] = hi_; }
+// Every second comparator takes its maximum off the ALU pipe: FMNMX (min / max) issues once per two
+// cycles per scheduler on the ALU pipe and the network is nothing but FMNMX, while the FMA pipe idles.
+// lo = fminf(a, b) is one of the two inputs bit for bit, so hi = bits(a) + bits(b) - bits(lo) in wrapping
+// integer arithmetic IS the other input, exactly (two IMAD on the FMA pipe; the multipliers +1 / -1 come
+// from the kernel arguments so that ptxas cannot fold them back into ALU-pipe IADD3).  Pixels holding a
+// NaN leave for the generic routine anyway.
+__device__ __forceinline__ int imad_fma_pipe(int a, int m, int c) {
+    int d;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(m), "r"(c));
+    return d;
+}
+#define CE_Y(i, j) { const float lo_ = fminf(x[i], x[j]);                                              \
+                     const int t_ = imad_fma_pipe(__float_as_int(x[i]), one_, __float_as_int(x[j]));   \
+                     x[j] = __int_as_float(imad_fma_pipe(__float_as_int(lo_), mone_, t_)); x[i] = lo_; }
 
 // Every 128 comparators the network has a CTA barrier: the 8 warps of a CTA walk the ~35 KB of
 // straight-line code together, so one instruction-cache fill serves all of them (ncu before:
 // `no_instruction` was the top stall of the median/MAD kernel).  The network is branch-free
 // and data-independent, so the barrier costs no load imbalance.
 #define SY_X() __syncthreads();
-template <int NB> __device__ __forceinline__ void sort_regs(float (&x)[NB]);
+template <int NB, bool MIX> __device__ __forceinline__ void sort_regs(float (&x)[NB], int one_, int mone_);
 #define APGPU_DEF_SORT(n) \
-    template <> __device__ __forceinline__ void sort_regs<n>(float (&x)[n]) { APGPU_SORTNET_##n(CE_X, SY_X) }
+    template <> __device__ __forceinline__ void sort_regs<n, true>(float (&x)[n], int one_, int mone_) { APGPU_SORTNET_##n(CE_X, CE_Y, SY_X) } \
+    template <> __device__ __forceinline__ void sort_regs<n, false>(float (&x)[n], int, int) { APGPU_SORTNET_##n(CE_X, CE_X, SY_X) }
 APGPU_DEF_SORT(4) APGPU_DEF_SORT(8) APGPU_DEF_SORT(12) APGPU_DEF_SORT(16) APGPU_DEF_SORT(20)
 APGPU_DEF_SORT(24) APGPU_DEF_SORT(32) APGPU_DEF_SORT(40) APGPU_DEF_SORT(48) APGPU_DEF_SORT(56)
 APGPU_DEF_SORT(64) APGPU_DEF_SORT(72) APGPU_DEF_SORT(80) APGPU_DEF_SORT(90) APGPU_DEF_SORT(100)
 APGPU_DEF_SORT(112) APGPU_DEF_SORT(128) APGPU_DEF_SORT(160) APGPU_DEF_SORT(200)
 
-template <int NB, int NLO, int MODE>
+template <int NB, int NLO, int MODE, bool MIX>
 __global__ void __launch_bounds__(STPB, (NB <= 32 ? 4 : (NB <= 100 ? 2 : 1)))
 stack_sorted_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_constant__ StackArgs a) {
     extern __shared__ float col[];       // MODE_MEDMAD1: [NB + 2][TPB] sorted columns + guard rows
@@ -64,7 +80,7 @@ stack_sorted_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_const
     }
     const bool nonfinite = (z != z);          // handled after the (barrier-carrying) sort
 
-    sort_regs<NB>(x);
+    sort_regs<NB, MIX>(x, a.one, a.minus_one);
     if (!valid) return;
     if (nonfinite) { generic_pixel<NB>(fp, a, p); return; }
 
@@ -142,18 +158,26 @@ stack_sorted_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_const
     write_pixel(a, p, mean, N - nk, unc, 0);
 }
 
-template <int NB, int NLO, int MODE>
-int launch_sorted(const float* const* frames, const StackArgs& a, cudaStream_t st) {
+template <int NB, int NLO, int MODE, bool MIX>
+int launch_sorted_mix(const float* const* frames, const StackArgs& a, cudaStream_t st) {
     FramePtrs<NB> fp;
     for (int i = 0; i < NB; ++i) fp.p[i] = i < a.N ? frames[i] : frames[0];   // padding: loaded, then replaced
     int64_t blocks = (a.npix + STPB - 1) / STPB;
     size_t smem = (MODE == MODE_MEDMAD1) ? (size_t)(NB + 2) * STPB * sizeof(float) : 0;
     if (smem > 48 * 1024)
-        APGPU_CUDA(cudaFuncSetAttribute(stack_sorted_kernel<NB, NLO, MODE>,
+        APGPU_CUDA(cudaFuncSetAttribute(stack_sorted_kernel<NB, NLO, MODE, MIX>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    stack_sorted_kernel<NB, NLO, MODE><<<(unsigned)blocks, STPB, smem, st>>>(fp, a);
+    stack_sorted_kernel<NB, NLO, MODE, MIX><<<(unsigned)blocks, STPB, smem, st>>>(fp, a);
     APGPU_LAUNCH_CHECK("stack_sorted_kernel");
     return APGPU_OK;
+}
+
+template <int NB, int NLO, int MODE>
+int launch_sorted(const float* const* frames, const StackArgs& a, cudaStream_t st) {
+    // the mixed-pipe comparators win everywhere (N=64 median 66 -> 81 %) except in the 255-register
+    // median/MAD kernel of the (160, 200] bucket (measured: tools/time_sorted.py)
+    constexpr bool MIX = !(NB > 160 && MODE == MODE_MEDMAD1);
+    return launch_sorted_mix<NB, NLO, MODE, MIX>(frames, a, st);
 }
 
 #define SO_CASE(NB_, NLO_) if (nb == NB_) return launch_sorted<NB_, NLO_, MODE>(frames, a, st);
