@@ -67,17 +67,32 @@ stack_sorted_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_const
     // frame 0 -- and replaced afterwards by uniform selects: no predicated loads / address arithmetic.
 #pragma unroll
     for (int i = 0; i < NB; ++i) x[i] = ld_stream(fp.p[i] + p32);
+    // Non-finite detection and, for the median/MAD mode, the sum of all samples (the mean when nothing
+    // is clipped, ~99 % of the pixels).  float64 output: frame-order float64 sum, bit-identical to
+    // np.nanmean.  float32 output: float32 sum of the samples shifted by the first frame (two packed
+    // accumulators on the FMA pipe instead of 100 F2F + 100 DADD; the result is within ~1e-8 relative of
+    // the float64 sum, far inside the 1e-6 contract).  Either sum is NaN / inf iff a sample is.
+    const float pivot = x[0];
+    float2 facc = make_float2(0.f, 0.f);
+    auto real_or = [&](int i, float pad) { return (i < NLO || i < N) ? x[i] : pad; };   // i < NLO: compile-time true
+    if (MODE == MODE_MEDMAD1) {
+        if (a.out_f64) {
 #pragma unroll
-    for (int i = 0; i < NB; ++i) {
-        float xa = x[i];
-        if (i >= NLO) {
-            const bool active = i < N;
-            xa = active ? xa : -0.f;                                           // x + (-0) == x bit for bit
-            x[i] = active ? x[i] : ((i - N < nneg) ? -INFINITY : INFINITY);
+            for (int i = 0; i < NB; ++i) sum_all = __dadd_rn(sum_all, (double)real_or(i, -0.f));   // x + (-0) == x
+            z = (float)(sum_all - sum_all);                                  // NaN iff a sample is NaN / inf
+        } else {
+            const float2 negpiv = make_float2(-pivot, -pivot);
+#pragma unroll
+            for (int i = 0; i + 1 < NB; i += 2)
+                facc = __fadd2_rn(facc, __fadd2_rn(make_float2(real_or(i, pivot), real_or(i + 1, pivot)), negpiv));
+            z = (facc.x + facc.y) * 0.f;                                     // NaN iff a sample is NaN / inf
         }
-        z = fmaf(xa, 0.f, z);
-        if (MODE == MODE_MEDMAD1) sum_all = __dadd_rn(sum_all, (double)xa);     // frame order, as nanmean
+    } else {
+#pragma unroll
+        for (int i = 0; i < NB; ++i) z = fmaf(real_or(i, 0.f), 0.f, z);
     }
+#pragma unroll
+    for (int i = NLO; i < NB; ++i) x[i] = (i < N) ? x[i] : ((i - N < nneg) ? -INFINITY : INFINITY);
     const bool nonfinite = (z != z);          // handled after the (barrier-carrying) sort
 
     sort_regs<NB, MIX>(x, a.one, a.minus_one);
@@ -140,7 +155,8 @@ stack_sorted_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_const
 #endif
     double mean;
     if (nk == N) {
-        mean = __ddiv_rn(sum_all, (double)N);
+        mean = a.out_f64 ? __ddiv_rn(sum_all, (double)N)
+                         : __dadd_rn((double)pivot, __ddiv_rn((double)(facc.x + facc.y), (double)N));
     } else {
         double acc = 0.0;
         for (int i = sa; i < sb; ++i) acc = __dadd_rn(acc, (double)s[i * STPB]);
