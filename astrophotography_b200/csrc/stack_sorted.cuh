@@ -1,6 +1,7 @@
 // Frame-stack reducer: sorted<NB, NLO, MODE> register-resident Batcher-network kernels.  See stack_common.cuh.
 #pragma once
 #include <stdlib.h>
+#include <string.h>
 #include "stack_common.cuh"
 #include "sort_networks.inc"
 
@@ -43,10 +44,15 @@ APGPU_DEF_SORT(24) APGPU_DEF_SORT(32) APGPU_DEF_SORT(40) APGPU_DEF_SORT(48) APGP
 APGPU_DEF_SORT(64) APGPU_DEF_SORT(72) APGPU_DEF_SORT(80) APGPU_DEF_SORT(90) APGPU_DEF_SORT(100)
 APGPU_DEF_SORT(112) APGPU_DEF_SORT(128) APGPU_DEF_SORT(160) APGPU_DEF_SORT(200)
 
-template <int NB, int NLO, int MODE, bool MIX>
+// TMA = true (equally spaced frames): the CTA's 256-pixel x N-frame tile arrives by ONE tensor-map bulk copy
+// into shared memory (the same region later holds the parked sorted columns) and the threads read their
+// column with LDS at immediate offsets: no LDG, no per-sample 64-bit address arithmetic on the ALU pipe
+// that the comparators saturate.
+template <int NB, int NLO, int MODE, bool MIX, bool TMA>
 __global__ void __launch_bounds__(STPB, (NB <= 32 ? 4 : (NB <= 100 ? 2 : 1)))
-stack_sorted_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_constant__ StackArgs a) {
-    extern __shared__ float col[];       // MODE_MEDMAD1: [NB + 2][TPB] sorted columns + guard rows
+stack_sorted_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FramePtrs<NB> fp,
+                    const __grid_constant__ StackArgs a) {
+    extern __shared__ __align__(128) float col[];   // [NB + 2][STPB]: TMA stage, then sorted columns + guard rows
     // no early exit: the sort contains CTA barriers.  Threads past the end redo the last pixel
     // and skip the write.
     const int64_t pend = a.pix0 + a.npix;
@@ -65,8 +71,22 @@ stack_sorted_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_const
     double sum_all = 0.0;
     // Padding slots (i >= N, only possible for i >= NLO) are loaded like real ones -- the host points them at
     // frame 0 -- and replaced afterwards by uniform selects: no predicated loads / address arithmetic.
+    if constexpr (TMA) {
+        uint64_t* bar = reinterpret_cast<uint64_t*>(col + (size_t)(NB + 2) * STPB);
+        if (threadIdx.x == 0) mbar_init(bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            // pixels past the end of the band are out of bounds of the tensor map: zero-filled, and counted
+            mbar_expect_tx(bar, (uint32_t)N * STPB * sizeof(float));
+            tma_load_2d(col, &tmap, (int32_t)(a.pix0 + (int64_t)blockIdx.x * STPB), 0, bar, l2_evict_first_policy());
+        }
+        while (!mbar_try_wait(bar, 0)) {}
 #pragma unroll
-    for (int i = 0; i < NB; ++i) x[i] = ld_stream(fp.p[i] + p32);
+        for (int i = 0; i < NB; ++i) x[i] = (i < NLO || i < N) ? col[i * STPB + threadIdx.x] : 0.f;
+    } else {
+#pragma unroll
+        for (int i = 0; i < NB; ++i) x[i] = ld_stream(fp.p[i] + p32);
+    }
     // Non-finite detection and, for the median/MAD mode, the sum of all samples (the mean when nothing
     // is clipped, ~99 % of the pixels).  float64 output: frame-order float64 sum, bit-identical to
     // np.nanmean.  float32 output: float32 sum of the samples shifted by the first frame (two packed
@@ -179,11 +199,26 @@ int launch_sorted_mix(const float* const* frames, const StackArgs& a, cudaStream
     FramePtrs<NB> fp;
     for (int i = 0; i < NB; ++i) fp.p[i] = i < a.N ? frames[i] : frames[0];   // padding: loaded, then replaced
     int64_t blocks = (a.npix + STPB - 1) / STPB;
-    size_t smem = (MODE == MODE_MEDMAD1) ? (size_t)(NB + 2) * STPB * sizeof(float) : 0;
-    if (smem > 48 * 1024)
-        APGPU_CUDA(cudaFuncSetAttribute(stack_sorted_kernel<NB, NLO, MODE, MIX>,
+    const size_t park = (size_t)(NB + 2) * STPB * sizeof(float);
+    CUtensorMap tmap;
+    const bool tma = stack_is_cube(frames, a.N, a.pix0 + a.npix) && a.pix0 % 4 == 0 &&
+                     encode_stack_tensor_map(&tmap, frames[0], (uint64_t)(a.pix0 + a.npix), a.N,
+                                             (uint64_t)((const char*)frames[1] - (const char*)frames[0]), STPB);
+    if (tma) {
+        const size_t smem = park + sizeof(uint64_t);
+        APGPU_CUDA(cudaFuncSetAttribute(stack_sorted_kernel<NB, NLO, MODE, MIX, true>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    stack_sorted_kernel<NB, NLO, MODE, MIX><<<(unsigned)blocks, STPB, smem, st>>>(fp, a);
+        stack_sorted_kernel<NB, NLO, MODE, MIX, true><<<(unsigned)blocks, STPB, smem, st>>>(tmap, fp, a);
+        stack_note_staging(1);
+    } else {
+        memset(&tmap, 0, sizeof(tmap));
+        const size_t smem = (MODE == MODE_MEDMAD1) ? park : 0;
+        if (smem > 48 * 1024)
+            APGPU_CUDA(cudaFuncSetAttribute(stack_sorted_kernel<NB, NLO, MODE, MIX, false>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        stack_sorted_kernel<NB, NLO, MODE, MIX, false><<<(unsigned)blocks, STPB, smem, st>>>(tmap, fp, a);
+        stack_note_staging(0);
+    }
     APGPU_LAUNCH_CHECK("stack_sorted_kernel");
     return APGPU_OK;
 }

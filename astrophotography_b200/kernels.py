@@ -47,7 +47,8 @@ def stack_kernel_name(n, method="average", k_lo=5.0, k_hi=5.0, maxiters=1, cen="
 
 
 def stack_last_staging():
-    """0 direct loads, 1 bulk copies, 2 cp.async, 3 tensor-map TMA, -1 not a meanclip launch."""
+    """-1 generic kernel, 0 direct loads, 1 CTA-wide bulk / tensor-map copies, 2 warp cp.async, 3 warp tensor-map TMA,
+    4 lane-split cp.async, 5 warp-cooperative swizzled tensor-map TMA (see include/apgpu.h)."""
     return int(_native.load().apgpu_stack_last_staging())
 
 

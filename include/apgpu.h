@@ -96,11 +96,17 @@ const char* apgpu_stack_kernel_name(int N, int method, double k_lo, double k_hi,
                                     int maxiters, int cen, int dev,
                                     int want_uncert, int out_is_f64, int flags);
 
-/* How the last apgpu_stack_reduce_f32 call of the calling thread fed the
- * meanclip kernel: -1 not a meanclip launch, 0 direct global loads, 1 CTA-wide
- * bulk copies, 2 warp-granular cp.async, 3 warp-granular tensor-map TMA, 4 lane-split cp.async (long stacks), 5 warp-cooperative swizzled tensor-map TMA (long stacks).  For
- * tests and the benchmark's bookkeeping (a requested staging falls back to 0
- * when its alignment / layout preconditions do not hold). */
+/* How the last apgpu_stack_reduce_f32 call of the calling thread fed its kernel
+ * (tests and the benchmark's bookkeeping):
+ *   -1 generic kernel
+ *    0 direct global loads (any frame pointers)
+ *    1 CTA-wide copies: bulk copies (meanclip, on request) / one tensor-map TMA box per
+ *      256-pixel tile (sorted kernels, equally spaced frames)
+ *    2 warp-granular cp.async pipeline
+ *    3 warp-granular tensor-map TMA pipeline (equally spaced frames; meanclip default)
+ *    4 lane-split cp.async (512 < N <= 1024)
+ *    5 warp-cooperative 128B-swizzled tensor-map TMA (100 < N <= 512)
+ * A requested staging falls back to 0 when its layout / alignment preconditions do not hold. */
 int apgpu_stack_last_staging(void);
 
 /* ------------------------------------------------------------------------
