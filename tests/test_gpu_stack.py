@@ -272,6 +272,36 @@ def test_meanclip_row_band_on_cube(cuda, n, shape, row0, nrows):
     assert (data[keep] == -7.0).all() and (nrej[keep] == 255).all()
 
 
+@pytest.mark.parametrize("n", [3, 4, 9, 30, 31, 64, 100, 127, 160, 200])
+@pytest.mark.parametrize("case", [c for c in FAST_CASES if c[-1].startswith("sorted")], ids=lambda c: "-".join(map(str, c)))
+def test_sorted_tensormap_staging(cuda, n, case):
+    """Equally spaced frames: the sorted kernels take their 256-pixel tiles through one tensor-map TMA box
+    (partial last tile, row band starting off a tile boundary); same results as the oracle."""
+    torch = cuda
+    from astrophotography_b200 import kernels
+    method, k_lo, k_hi, maxiters, cen, dev, family = case
+    st = _stack(n, (11, 76), seed=90 + n, quantise=(n % 2 == 1))     # 836 pixels: 3 full tiles + 68 pixels
+    exp = _oracle(st, method, k_lo, k_hi, maxiters, cen, dev)
+    for out_f64 in (False, True):
+        got = _run(torch, st, method=method, k_lo=k_lo, k_hi=k_hi, maxiters=maxiters, cen=cen, dev=dev, out_f64=out_f64)
+        assert kernels.stack_last_staging() == 1
+        assert np.array_equal(got["nrej"].astype(np.int64), exp["nrej"])
+        if family == "sorted_median":
+            e = exp["data"] if out_f64 else exp["data"].astype(np.float32)
+            assert bits_equal(got["data"], e)
+        else:
+            _assert_close_data(got["data"].astype(np.float64), exp["data"], RTOL32 if not out_f64 else 1e-13, 12.0)
+    # a row band (rows 2..8) of the same cube
+    cube = torch.from_numpy(st).cuda()
+    out = {"data": torch.full((11, 76), -7.0, dtype=torch.float32, device="cuda")}
+    kernels.stack_reduce(cube, method=method, k_lo=k_lo, k_hi=k_hi, maxiters=maxiters, cen=cen, dev=dev,
+                         row0=2, nrows=7, out=out, want_nrej=False)
+    torch.cuda.synchronize()
+    d = out["data"].cpu().numpy()
+    _assert_close_data(d[2:9].astype(np.float64), exp["data"][2:9], RTOL32, 12.0)
+    assert (d[:2] == -7.0).all() and (d[9:] == -7.0).all()
+
+
 def test_fast_uncert(cuda):
     torch = cuda
     st = _stack(30, (8, 64), seed=5)
