@@ -115,6 +115,15 @@ int stack_dispatch_meanclip(int nb, const float* const* frames, const StackArgs&
     return stack_dispatch_meanclip_hi(nb, frames, a, st, flags);
 }
 
+int stack_median_tiles_per_cta() {
+    static int v = 0;
+    if (!v) {
+        const char* e = getenv("APGPU_MEDIAN_TILES_PER_CTA");   // tuning knob
+        int x = e ? atoi(e) : 0;
+        v = (x >= 1 && x <= 4096) ? x : 8;
+    }
+    return v;
+}
 int stack_coop_box_rows_max() {
     static int v = 0;
     if (!v) {

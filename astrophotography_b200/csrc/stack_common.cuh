@@ -295,6 +295,7 @@ bool encode_stack_tensor_map(CUtensorMap* tmap, const float* base, uint64_t npix
 void stack_note_staging(int staging);
 int stack_tmap_tiles_per_warp();
 int stack_coop_box_rows_max();
+int stack_median_tiles_per_cta();
 
 // cross-translation-unit launchers (one .cu per kernel family so that nvcc compiles them in parallel)
 int stack_launch_generic(const float* const* frames, const StackArgs& a, cudaStream_t st);

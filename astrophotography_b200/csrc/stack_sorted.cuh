@@ -194,6 +194,60 @@ stack_sorted_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     write_pixel(a, p, mean, N - nk, unc, 0);
 }
 
+// Plain median on equally spaced frames: the shared-memory stage is free again as soon as the threads
+// hold their samples, so each CTA walks a run of consecutive 256-pixel tiles and the tensor-map copy of the
+// NEXT tile is issued before the sort of the current one starts -- its HBM latency hides behind the
+// ~1700 comparators (the one-tile-per-CTA kernel spent 18 % of its stall samples waiting for its tile).
+template <int NB, int NLO, bool MIX>
+__global__ void __launch_bounds__(STPB, (NB <= 32 ? 4 : (NB <= 100 ? 2 : 1)))
+stack_median_tmap_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FramePtrs<NB> fp,
+                         const __grid_constant__ StackArgs a) {
+    extern __shared__ __align__(128) float col[];   // [NB][STPB] stage
+    uint64_t* bar = reinterpret_cast<uint64_t*>(col + (size_t)NB * STPB);
+    const int N = a.N;
+    const int npad = NB - N;
+    const int nneg = npad >> 1;          // -inf pads; the other npad-nneg are +inf
+    const int pix0 = (int)a.pix0, pend = pix0 + (int)a.npix;     // the host takes this path below 2^31 pixels
+    const int ntiles = (int)((a.npix + STPB - 1) / STPB);
+    int tile = (int)blockIdx.x * a.tiles_per_warp;
+    const int tile_end = min(tile + a.tiles_per_warp, ntiles);
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    __syncthreads();
+    auto issue = [&](int t) {
+        // pixels past the end of the band are out of bounds of the tensor map: zero-filled, and counted
+        mbar_expect_tx(bar, (uint32_t)N * STPB * sizeof(float));
+        tma_load_2d(col, &tmap, pix0 + t * STPB, 0, bar, l2_evict_first_policy());
+    };
+    if (threadIdx.x == 0 && tile < tile_end) issue(tile);
+    uint32_t parity = 0;
+    for (; tile < tile_end; ++tile) {
+        while (!mbar_try_wait(bar, parity)) {}
+        parity ^= 1u;
+        float x[NB];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) x[i] = (i < NLO || i < N) ? col[i * STPB + threadIdx.x] : 0.f;
+        float z = 0.f;
+#pragma unroll
+        for (int i = 0; i < NB; ++i) z = fmaf(x[i], 0.f, z);                  // NaN iff a sample is NaN / inf
+        __syncthreads();                 // every thread has consumed its column: the stage can be refilled
+        if (threadIdx.x == 0 && tile + 1 < tile_end) issue(tile + 1);
+#pragma unroll
+        for (int i = NLO; i < NB; ++i) x[i] = (i < N) ? x[i] : ((i - N < nneg) ? -INFINITY : INFINITY);
+        sort_regs<NB, MIX>(x, a.one, a.minus_one);
+        const int p = pix0 + tile * STPB + threadIdx.x;
+        if (p < pend) {
+            if (z != z) {
+                generic_pixel<NB>(fp, a, (int64_t)p);
+            } else {
+                constexpr int C = NB / 2;
+                const double med = (N & 1) ? (double)x[C - 1]
+                                           : __dmul_rn(__dadd_rn((double)x[C - 1], (double)x[C]), 0.5);
+                write_pixel(a, (int64_t)p, med, 0, (double)NAN, 0);
+            }
+        }
+    }
+}
+
 template <int NB, int NLO, int MODE, bool MIX>
 int launch_sorted_mix(const float* const* frames, const StackArgs& a, cudaStream_t st) {
     FramePtrs<NB> fp;
@@ -204,7 +258,16 @@ int launch_sorted_mix(const float* const* frames, const StackArgs& a, cudaStream
     const bool tma = stack_is_cube(frames, a.N, a.pix0 + a.npix) && a.pix0 % 4 == 0 &&
                      encode_stack_tensor_map(&tmap, frames[0], (uint64_t)(a.pix0 + a.npix), a.N,
                                              (uint64_t)((const char*)frames[1] - (const char*)frames[0]), STPB);
-    if (tma) {
+    if (tma && MODE == MODE_MED) {
+        StackArgs at = a;
+        at.tiles_per_warp = stack_median_tiles_per_cta();
+        const int64_t grid = (blocks + at.tiles_per_warp - 1) / at.tiles_per_warp;
+        const size_t smem = (size_t)NB * STPB * sizeof(float) + sizeof(uint64_t);
+        APGPU_CUDA(cudaFuncSetAttribute(stack_median_tmap_kernel<NB, NLO, MIX>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        stack_median_tmap_kernel<NB, NLO, MIX><<<(unsigned)grid, STPB, smem, st>>>(tmap, fp, at);
+        stack_note_staging(1);
+    } else if (tma) {
         const size_t smem = park + sizeof(uint64_t);
         APGPU_CUDA(cudaFuncSetAttribute(stack_sorted_kernel<NB, NLO, MODE, MIX, true>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
