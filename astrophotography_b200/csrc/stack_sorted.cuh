@@ -48,150 +48,175 @@ APGPU_DEF_SORT(112) APGPU_DEF_SORT(128) APGPU_DEF_SORT(160) APGPU_DEF_SORT(200)
 // into shared memory (the same region later holds the parked sorted columns) and the threads read their
 // column with LDS at immediate offsets: no LDG, no per-sample 64-bit address arithmetic on the ALU pipe
 // that the comparators saturate.
-template <int NB, int NLO, int MODE, bool MIX, bool TMA>
-__global__ void __launch_bounds__(STPB, (NB <= 32 ? 4 : (NB <= 100 ? 2 : 1)))
+template <int NB, int NLO, int MODE, bool MIX, bool TMA, bool LOOP>
+__global__ void __launch_bounds__(STPB, (NB <= 32 ? (LOOP ? 3 : 4) : (NB <= 100 ? 2 : 1)))
 stack_sorted_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FramePtrs<NB> fp,
                     const __grid_constant__ StackArgs a) {
-    extern __shared__ __align__(128) float col[];   // [NB + 2][STPB]: TMA stage, then sorted columns + guard rows
-    // no early exit: the sort contains CTA barriers.  Threads past the end redo the last pixel
-    // and skip the write.
-    const int64_t pend = a.pix0 + a.npix;
-    int64_t p = a.pix0 + (int64_t)blockIdx.x * STPB + threadIdx.x;
-    const bool valid = p < pend;
-    if (!valid) p = pend - 1;
+    // [NB + 2][STPB] sorted columns + guard rows (median/MAD mode); the TMA stage is the same region
+    // (one tile per CTA), or -- LOOP -- its own [NB][STPB] region behind it, so that each CTA walks a run of
+    // tiles and the NEXT tile's copy is issued before the current tile is sorted (measured for the
+    // median/MAD mode at N = 30: 0.611 -> 0.605 ms, i.e. nothing -- not instantiated; the plain median has
+    // its own prefetching kernel below, where it does pay)
+    extern __shared__ __align__(128) float col[];
+    constexpr size_t PARK = (size_t)(NB + 2) * STPB;
+    float* const stage = LOOP ? col + PARK : col;
+    uint64_t* const bar = reinterpret_cast<uint64_t*>(col + PARK + (LOOP ? (size_t)NB * STPB : 0));
     const int N = a.N;
     // Pad to NB with -inf / +inf split so that the real samples sit centred in
     // the sorted array: the median is then at the compile-time index NB/2-1
     // (and NB/2 for even N) whatever N is.
     const int npad = NB - N;
     const int nneg = npad >> 1;          // -inf pads; the other npad-nneg are +inf
-    const uint32_t p32 = (uint32_t)p;    // host guarantees H*W < 2^32: one IMAD.WIDE per address
-    float x[NB];
-    float z = 0.f;
-    double sum_all = 0.0;
-    // Padding slots (i >= N, only possible for i >= NLO) are loaded like real ones -- the host points them at
-    // frame 0 -- and replaced afterwards by uniform selects: no predicated loads / address arithmetic.
+    const int64_t pend = a.pix0 + a.npix;
+    const int ntiles = (int)((a.npix + STPB - 1) / STPB);
+    int tile = LOOP ? (int)blockIdx.x * a.tiles_per_warp : (int)blockIdx.x;
+    const int tile_end = LOOP ? min(tile + a.tiles_per_warp, ntiles) : tile + 1;
+    auto issue = [&](int t) {
+        // pixels past the end of the band are out of bounds of the tensor map: zero-filled, and counted
+        mbar_expect_tx(bar, (uint32_t)N * STPB * sizeof(float));
+        tma_load_2d(stage, &tmap, (int32_t)(a.pix0 + (int64_t)t * STPB), 0, bar, l2_evict_first_policy());
+    };
     if constexpr (TMA) {
-        uint64_t* bar = reinterpret_cast<uint64_t*>(col + (size_t)(NB + 2) * STPB);
         if (threadIdx.x == 0) mbar_init(bar, 1);
         __syncthreads();
-        if (threadIdx.x == 0) {
-            // pixels past the end of the band are out of bounds of the tensor map: zero-filled, and counted
-            mbar_expect_tx(bar, (uint32_t)N * STPB * sizeof(float));
-            tma_load_2d(col, &tmap, (int32_t)(a.pix0 + (int64_t)blockIdx.x * STPB), 0, bar, l2_evict_first_policy());
-        }
-        while (!mbar_try_wait(bar, 0)) {}
-#pragma unroll
-        for (int i = 0; i < NB; ++i) x[i] = (i < NLO || i < N) ? col[i * STPB + threadIdx.x] : 0.f;
-    } else {
-#pragma unroll
-        for (int i = 0; i < NB; ++i) x[i] = ld_stream(fp.p[i] + p32);
+        if (threadIdx.x == 0 && tile < tile_end) issue(tile);
     }
-    // Non-finite detection and, for the median/MAD mode, the sum of all samples (the mean when nothing
-    // is clipped, ~99 % of the pixels).  float64 output: frame-order float64 sum, bit-identical to
-    // np.nanmean.  float32 output: float32 sum of the samples shifted by the first frame (two packed
-    // accumulators on the FMA pipe instead of 100 F2F + 100 DADD; the result is within ~1e-8 relative of
-    // the float64 sum, far inside the 1e-6 contract).  Either sum is NaN / inf iff a sample is.
-    const float pivot = x[0];
-    float2 facc = make_float2(0.f, 0.f);
-    auto real_or = [&](int i, float pad) { return (i < NLO || i < N) ? x[i] : pad; };   // i < NLO: compile-time true
-    if (MODE == MODE_MEDMAD1) {
-        if (a.out_f64) {
+    uint32_t parity = 0;
+    for (; tile < tile_end; ++tile) {
+        // no early exit: the sort contains CTA barriers.  Threads past the end redo the last pixel
+        // and skip the write.
+        int64_t p = a.pix0 + (int64_t)tile * STPB + threadIdx.x;
+        const bool valid = p < pend;
+        if (!valid) p = pend - 1;
+        const uint32_t p32 = (uint32_t)p;    // host guarantees H*W < 2^32: one IMAD.WIDE per address
+        float x[NB];
+        float z = 0.f;
+        double sum_all = 0.0;
+        // Padding slots (i >= N, only possible for i >= NLO) are loaded like real ones -- the host points
+        // them at frame 0 -- and replaced afterwards by uniform selects: no predicated loads.
+        if constexpr (TMA) {
+            while (!mbar_try_wait(bar, parity)) {}
+            parity ^= 1u;
 #pragma unroll
-            for (int i = 0; i < NB; ++i) sum_all = __dadd_rn(sum_all, (double)real_or(i, -0.f));   // x + (-0) == x
-            z = (float)(sum_all - sum_all);                                  // NaN iff a sample is NaN / inf
+            for (int i = 0; i < NB; ++i) x[i] = (i < NLO || i < N) ? stage[i * STPB + threadIdx.x] : 0.f;
         } else {
-            const float2 negpiv = make_float2(-pivot, -pivot);
 #pragma unroll
-            for (int i = 0; i + 1 < NB; i += 2)
-                facc = __fadd2_rn(facc, __fadd2_rn(make_float2(real_or(i, pivot), real_or(i + 1, pivot)), negpiv));
-            z = (facc.x + facc.y) * 0.f;                                     // NaN iff a sample is NaN / inf
+            for (int i = 0; i < NB; ++i) x[i] = ld_stream(fp.p[i] + p32);
         }
-    } else {
+        // Non-finite detection and, for the median/MAD mode, the sum of all samples (the mean when nothing
+        // is clipped, ~99 % of the pixels).  float64 output: frame-order float64 sum, bit-identical to
+        // np.nanmean.  float32 output: float32 sum of the samples shifted by the first frame (two packed
+        // accumulators on the FMA pipe instead of 100 F2F + 100 DADD; the result is within ~1e-8 relative of
+        // the float64 sum, far inside the 1e-6 contract).  Either sum is NaN / inf iff a sample is.
+        const float pivot = x[0];
+        float2 facc = make_float2(0.f, 0.f);
+        auto real_or = [&](int i, float pad) { return (i < NLO || i < N) ? x[i] : pad; };   // i < NLO: compile-time true
+        if (MODE == MODE_MEDMAD1) {
+            if (a.out_f64) {
 #pragma unroll
-        for (int i = 0; i < NB; ++i) z = fmaf(real_or(i, 0.f), 0.f, z);
-    }
+                for (int i = 0; i < NB; ++i) sum_all = __dadd_rn(sum_all, (double)real_or(i, -0.f));   // x + (-0) == x
+                z = (float)(sum_all - sum_all);                                  // NaN iff a sample is NaN / inf
+            } else {
+                const float2 negpiv = make_float2(-pivot, -pivot);
 #pragma unroll
-    for (int i = NLO; i < NB; ++i) x[i] = (i < N) ? x[i] : ((i - N < nneg) ? -INFINITY : INFINITY);
-    const bool nonfinite = (z != z);          // handled after the (barrier-carrying) sort
-
-    sort_regs<NB, MIX>(x, a.one, a.minus_one);
-    if (!valid) return;
-    if (nonfinite) { generic_pixel<NB>(fp, a, p); return; }
-
-    constexpr int C = NB / 2;
-    const double med = (N & 1) ? (double)x[C - 1]
-                               : __dmul_rn(__dadd_rn((double)x[C - 1], (double)x[C]), 0.5);
-    if (MODE == MODE_MED) {
-        write_pixel(a, p, med, 0, (double)NAN, 0);
-        return;
-    }
-
-    // Park the sorted column in shared memory ([row][thread]: conflict-free for
-    // any per-thread row index) for the data-dependent selection below.  Row 0
-    // and row NB+1 are -inf / +inf guards, so together with the +-inf padding
-    // every row outside the real samples has an infinite deviation from the
-    // median and the merge below needs no bounds checks.
-    float* s = col + threadIdx.x + STPB;          // s[i * STPB] = sorted sample i, i in [-1, NB]
-    s[-STPB] = -INFINITY;
-    s[NB * STPB] = INFINITY;
+                for (int i = 0; i + 1 < NB; i += 2)
+                    facc = __fadd2_rn(facc, __fadd2_rn(make_float2(real_or(i, pivot), real_or(i + 1, pivot)), negpiv));
+                z = (facc.x + facc.y) * 0.f;                                     // NaN iff a sample is NaN / inf
+            }
+        } else {
 #pragma unroll
-    for (int i = 0; i < NB; ++i) s[i * STPB] = x[i];
-    const int base = nneg;               // real samples occupy rows [base, base + N)
-    // MAD = median of |x - med|.  Left of the median the deviations grow towards row
-    // `base`, right of it towards row `base+N`: two sorted lists,
-    //     L[j] = med - s[l0 - j]   (j = 0 .. nL-1),   R[j] = s[l0 + 1 + j] - med   (j = 0 .. nR-1),
-    // whose (k+1)-th smallest element is found by bisecting on how many come from L
-    // (O(log N) shared-memory reads, float64, exact).  Guard rows / +-inf padding give
-    // every out-of-range index an infinite deviation.
-    const int l0 = base + ((N - 1) >> 1);
-    const int nL = l0 - base + 1, nR = N - nL;
-    auto devL = [&](int j) { return fabs(__dsub_rn((double)s[(l0 - j) * STPB], med)); };
-    auto devR = [&](int j) { return fabs(__dsub_rn((double)s[(l0 + 1 + j) * STPB], med)); };
-    const int k1 = (N - 1) >> 1;                       // 0-based rank of the lower middle deviation
-    int lo_i = k1 + 1 - nR > 0 ? k1 + 1 - nR : 0;
-    int hi_i = k1 + 1 < nL ? k1 + 1 : nL;
-    while (lo_i < hi_i) {
-        const int mid = (lo_i + hi_i) >> 1;
-        if (devL(mid) < devR(k1 - mid)) lo_i = mid + 1; else hi_i = mid;
-    }
-    // lo_i samples of the k1+1 smallest deviations come from L, k1+1-lo_i from R
-    const double la = lo_i > 0 ? devL(lo_i - 1) : -1.0;
-    const double ra = (k1 - lo_i) >= 0 ? devR(k1 - lo_i) : -1.0;
-    const double d1 = la > ra ? la : ra;
-    const double lb = devL(lo_i), rb = devR(k1 + 1 - lo_i);      // the next deviation up (inf past the ends)
-    const double d2 = lb < rb ? lb : rb;
-    const double mad = (N & 1) ? d1 : __dmul_rn(__dadd_rn(d1, d2), 0.5);
-    const double sd = __dmul_rn(MAD_TO_STD, mad);
-    const double lo = __dsub_rn(med, __dmul_rn(sd, a.klo));
-    const double hi = __dadd_rn(med, __dmul_rn(sd, a.khi));
-    int sa = base, sb = base + N;
-    while (sa < sb && (double)s[sa * STPB] < lo) ++sa;
-    while (sa < sb && (double)s[(sb - 1) * STPB] > hi) --sb;
-    const int nk = sb - sa;
+            for (int i = 0; i < NB; ++i) z = fmaf(real_or(i, 0.f), 0.f, z);
+        }
+#pragma unroll
+        for (int i = NLO; i < NB; ++i) x[i] = (i < N) ? x[i] : ((i - N < nneg) ? -INFINITY : INFINITY);
+        const bool nonfinite = (z != z);          // handled after the (barrier-carrying) sort
+
+
+        if constexpr (LOOP) {
+            __syncthreads();             // every thread has consumed its column (z depends on all of it)
+            if (threadIdx.x == 0 && tile + 1 < tile_end) issue(tile + 1);
+        }
+        sort_regs<NB, MIX>(x, a.one, a.minus_one);
+        [&]() {
+            if (!valid) return;
+            if (nonfinite) { generic_pixel<NB>(fp, a, p); return; }
+
+            constexpr int C = NB / 2;
+            const double med = (N & 1) ? (double)x[C - 1]
+                                       : __dmul_rn(__dadd_rn((double)x[C - 1], (double)x[C]), 0.5);
+            if (MODE == MODE_MED) {
+                write_pixel(a, p, med, 0, (double)NAN, 0);
+                return;
+            }
+
+            // Park the sorted column in shared memory ([row][thread]: conflict-free for
+            // any per-thread row index) for the data-dependent selection below.  Row 0
+            // and row NB+1 are -inf / +inf guards, so together with the +-inf padding
+            // every row outside the real samples has an infinite deviation from the
+            // median and the merge below needs no bounds checks.
+            float* s = col + threadIdx.x + STPB;          // s[i * STPB] = sorted sample i, i in [-1, NB]
+            s[-STPB] = -INFINITY;
+            s[NB * STPB] = INFINITY;
+#pragma unroll
+            for (int i = 0; i < NB; ++i) s[i * STPB] = x[i];
+            const int base = nneg;               // real samples occupy rows [base, base + N)
+            // MAD = median of |x - med|.  Left of the median the deviations grow towards row
+            // `base`, right of it towards row `base+N`: two sorted lists,
+            //     L[j] = med - s[l0 - j]   (j = 0 .. nL-1),   R[j] = s[l0 + 1 + j] - med   (j = 0 .. nR-1),
+            // whose (k+1)-th smallest element is found by bisecting on how many come from L
+            // (O(log N) shared-memory reads, float64, exact).  Guard rows / +-inf padding give
+            // every out-of-range index an infinite deviation.
+            const int l0 = base + ((N - 1) >> 1);
+            const int nL = l0 - base + 1, nR = N - nL;
+            auto devL = [&](int j) { return fabs(__dsub_rn((double)s[(l0 - j) * STPB], med)); };
+            auto devR = [&](int j) { return fabs(__dsub_rn((double)s[(l0 + 1 + j) * STPB], med)); };
+            const int k1 = (N - 1) >> 1;                       // 0-based rank of the lower middle deviation
+            int lo_i = k1 + 1 - nR > 0 ? k1 + 1 - nR : 0;
+            int hi_i = k1 + 1 < nL ? k1 + 1 : nL;
+            while (lo_i < hi_i) {
+                const int mid = (lo_i + hi_i) >> 1;
+                if (devL(mid) < devR(k1 - mid)) lo_i = mid + 1; else hi_i = mid;
+            }
+            // lo_i samples of the k1+1 smallest deviations come from L, k1+1-lo_i from R
+            const double la = lo_i > 0 ? devL(lo_i - 1) : -1.0;
+            const double ra = (k1 - lo_i) >= 0 ? devR(k1 - lo_i) : -1.0;
+            const double d1 = la > ra ? la : ra;
+            const double lb = devL(lo_i), rb = devR(k1 + 1 - lo_i);      // the next deviation up (inf past the ends)
+            const double d2 = lb < rb ? lb : rb;
+            const double mad = (N & 1) ? d1 : __dmul_rn(__dadd_rn(d1, d2), 0.5);
+            const double sd = __dmul_rn(MAD_TO_STD, mad);
+            const double lo = __dsub_rn(med, __dmul_rn(sd, a.klo));
+            const double hi = __dadd_rn(med, __dmul_rn(sd, a.khi));
+            int sa = base, sb = base + N;
+            while (sa < sb && (double)s[sa * STPB] < lo) ++sa;
+            while (sa < sb && (double)s[(sb - 1) * STPB] > hi) --sb;
+            const int nk = sb - sa;
 #ifdef APGPU_DEBUG_MEDMAD
-    if (p == a.pix0) printf("dbg N=%d NB=%d base=%d med=%.6f d1=%.6f d2=%.6f mad=%.6f lo=%.6f hi=%.6f sa=%d sb=%d klo=%f\n",
-        N, NB, base, med, d1, d2, mad, lo, hi, sa, sb, a.klo);
+            if (p == a.pix0) printf("dbg N=%d NB=%d base=%d med=%.6f d1=%.6f d2=%.6f mad=%.6f lo=%.6f hi=%.6f sa=%d sb=%d klo=%f\n",
+                N, NB, base, med, d1, d2, mad, lo, hi, sa, sb, a.klo);
 #endif
-    double mean;
-    if (nk == N) {
-        mean = a.out_f64 ? __ddiv_rn(sum_all, (double)N)
-                         : __dadd_rn((double)pivot, __ddiv_rn((double)(facc.x + facc.y), (double)N));
-    } else {
-        double acc = 0.0;
-        for (int i = sa; i < sb; ++i) acc = __dadd_rn(acc, (double)s[i * STPB]);
-        mean = __ddiv_rn(acc, (double)nk);      // nk >= 1: the median itself always survives
+            double mean;
+            if (nk == N) {
+                mean = a.out_f64 ? __ddiv_rn(sum_all, (double)N)
+                                 : __dadd_rn((double)pivot, __ddiv_rn((double)(facc.x + facc.y), (double)N));
+            } else {
+                double acc = 0.0;
+                for (int i = sa; i < sb; ++i) acc = __dadd_rn(acc, (double)s[i * STPB]);
+                mean = __ddiv_rn(acc, (double)nk);      // nk >= 1: the median itself always survives
+            }
+            double unc = (double)NAN;
+            if (a.uncert) {
+                double acc = 0.0;
+                for (int i = sa; i < sb; ++i) {
+                    double d = __dsub_rn((double)s[i * STPB], mean);
+                    acc = __dadd_rn(acc, __dmul_rn(d, d));
+                }
+                unc = __ddiv_rn(__dsqrt_rn(__ddiv_rn(acc, (double)nk)), __dsqrt_rn((double)nk));
+            }
+            write_pixel(a, p, mean, N - nk, unc, 0);
+
+        }();
     }
-    double unc = (double)NAN;
-    if (a.uncert) {
-        double acc = 0.0;
-        for (int i = sa; i < sb; ++i) {
-            double d = __dsub_rn((double)s[i * STPB], mean);
-            acc = __dadd_rn(acc, __dmul_rn(d, d));
-        }
-        unc = __ddiv_rn(__dsqrt_rn(__ddiv_rn(acc, (double)nk)), __dsqrt_rn((double)nk));
-    }
-    write_pixel(a, p, mean, N - nk, unc, 0);
 }
 
 // Plain median on equally spaced frames: the shared-memory stage is free again as soon as the threads
@@ -258,7 +283,7 @@ int launch_sorted_mix(const float* const* frames, const StackArgs& a, cudaStream
     const bool tma = stack_is_cube(frames, a.N, a.pix0 + a.npix) && a.pix0 % 4 == 0 &&
                      encode_stack_tensor_map(&tmap, frames[0], (uint64_t)(a.pix0 + a.npix), a.N,
                                              (uint64_t)((const char*)frames[1] - (const char*)frames[0]), STPB);
-    if (tma && MODE == MODE_MED) {
+    if (tma && MODE == MODE_MED) {   // (the other modes never take this branch)
         StackArgs at = a;
         at.tiles_per_warp = stack_median_tiles_per_cta();
         const int64_t grid = (blocks + at.tiles_per_warp - 1) / at.tiles_per_warp;
@@ -269,17 +294,17 @@ int launch_sorted_mix(const float* const* frames, const StackArgs& a, cudaStream
         stack_note_staging(1);
     } else if (tma) {
         const size_t smem = park + sizeof(uint64_t);
-        APGPU_CUDA(cudaFuncSetAttribute(stack_sorted_kernel<NB, NLO, MODE, MIX, true>,
+        APGPU_CUDA(cudaFuncSetAttribute(stack_sorted_kernel<NB, NLO, MODE, MIX, true, false>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        stack_sorted_kernel<NB, NLO, MODE, MIX, true><<<(unsigned)blocks, STPB, smem, st>>>(tmap, fp, a);
+        stack_sorted_kernel<NB, NLO, MODE, MIX, true, false><<<(unsigned)blocks, STPB, smem, st>>>(tmap, fp, a);
         stack_note_staging(1);
     } else {
         memset(&tmap, 0, sizeof(tmap));
         const size_t smem = (MODE == MODE_MEDMAD1) ? park : 0;
         if (smem > 48 * 1024)
-            APGPU_CUDA(cudaFuncSetAttribute(stack_sorted_kernel<NB, NLO, MODE, MIX, false>,
+            APGPU_CUDA(cudaFuncSetAttribute(stack_sorted_kernel<NB, NLO, MODE, MIX, false, false>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        stack_sorted_kernel<NB, NLO, MODE, MIX, false><<<(unsigned)blocks, STPB, smem, st>>>(tmap, fp, a);
+        stack_sorted_kernel<NB, NLO, MODE, MIX, false, false><<<(unsigned)blocks, STPB, smem, st>>>(tmap, fp, a);
         stack_note_staging(0);
     }
     APGPU_LAUNCH_CHECK("stack_sorted_kernel");
