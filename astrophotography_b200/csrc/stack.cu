@@ -194,6 +194,15 @@ extern "C" const char* apgpu_stack_kernel_name(int N, int method, double k_lo, d
     (void)out_is_f64;
     const Bucket* b = nullptr;
     Family f = choose_family(N, method, k_lo, k_hi, maxiters, cen, dev, want_uncert != 0, flags, &b);
+    // long kappa-sigma stacks: the name of the default path on equally spaced frames (other layouts fall back
+    // to the pointer-table kernels named below -- apgpu_stack_last_staging() tells which one ran)
+    if (N > 100 && meanclip_eligible(N, method, k_lo, k_hi, maxiters, cen, dev, flags) &&
+        !(flags & (APGPU_STACK_DIRECT_LOADS | APGPU_STACK_USE_TMA | APGPU_STACK_USE_CPASYNC | APGPU_STACK_PREFER_SHARED |
+                   APGPU_STACK_PREFER_REGISTERS))) {
+        if (N <= 512) snprintf(g_kname, sizeof(g_kname), "meanclip_coop<%d>", N <= 128 ? 2 : (N <= 256 ? 4 : 8));
+        else snprintf(g_kname, sizeof(g_kname), "meanclip_split<8>");
+        return g_kname;
+    }
     switch (f) {
         case FAM_MEANCLIP: snprintf(g_kname, sizeof(g_kname), "meanclip<%d>", b->nb); break;
         case FAM_MEANCLIP_SMEM: snprintf(g_kname, sizeof(g_kname), "meanclip_smem"); break;

@@ -41,11 +41,15 @@ def test_kernel_selection_is_host_logic():
     assert kernels.stack_kernel_name(100).startswith("sorted_medmad1<100>")
     assert kernels.stack_kernel_name(100, "average", 3, 3, 5, "mean", "std") == "meanclip<100>"
     assert kernels.stack_kernel_name(100, "average", 3, 3, 5, "mean", "std", prefer="shared") == "meanclip_smem"
-    assert kernels.stack_kernel_name(300, "average", 3, 3, 5, "mean", "std") == "meanclip_smem"
+    assert kernels.stack_kernel_name(300, "average", 3, 3, 5, "mean", "std") == "meanclip_coop<8>"
+    assert kernels.stack_kernel_name(300, "average", 3, 3, 5, "mean", "std", prefer="shared") == "meanclip_smem"
+    assert kernels.stack_kernel_name(200, "average", 3, 3, 5, "mean", "std") == "meanclip_coop<4>"
+    assert kernels.stack_kernel_name(1000, "average", 3, 3, 5, "mean", "std") == "meanclip_split<8>"
     assert kernels.stack_kernel_name(30, "median", maxiters=0) == "sorted_median<32>"
     assert kernels.stack_kernel_name(30, "median", maxiters=0, want_uncert=True).startswith("generic")
     assert kernels.stack_kernel_name(30, force_generic=True).startswith("generic")
-    assert kernels.stack_kernel_name(600, "average", 3, 3, 5, "mean", "std").startswith("generic")
+    assert kernels.stack_kernel_name(600, "average", 3, 3, 5, "mean", "std") == "meanclip_split<8>"
+    assert kernels.stack_kernel_name(600, "average", 3, 3, 5, "mean", "std", prefer="registers").startswith("generic")
 
 
 def test_argument_errors_surface_without_gpu():
