@@ -9,23 +9,25 @@
 // frame, so every HBM access is a full coalesced line and each input byte is
 // read exactly once (4*N + 5 B per pixel algorithmic traffic).
 //
-// Three kernel families behind one entry point:
-//   generic<CAP>      every parameter combination, N <= 1024.  float64
-//                     arithmetic in the oracle's operation order (explicitly
-//                     rounded intrinsics, no FMA contraction): bit-identical to
-//                     the numpy restatement.  Values live in local memory.
-//   meanclip<NB,NLO>  iterative kappa-sigma clip about the MEAN with the
-//                     population STD, then the mean of the survivors.
-//                     Register-resident (N <= 200), float32 arithmetic on
-//                     pivot-shifted values with a rigorous error bound: a pixel
-//                     whose decision could differ from the float64 oracle
-//                     (a sample within the bound of a clip threshold) is redone
-//                     by the generic routine, so rejection maps are identical.
-//   sorted<NB,MODE>   register-resident Batcher merge-exchange network
-//                     (N <= 128): plain median (MODE_MED), or the reference's
-//                     ApMasterCal setting -- one median/MAD clip pass then the
-//                     mean (MODE_MEDMAD1) -- with the sorted column parked in
-//                     shared memory for the data-dependent MAD selection.
+// Kernel families behind one entry point (one translation unit per family / instantiation group):
+//   generic<CAP>        every parameter combination, N <= 1024.  float64 arithmetic in the
+//                       oracle's operation order (explicitly rounded intrinsics, no FMA
+//                       contraction): bit-identical to the numpy restatement.  Local memory.
+//   meanclip<NB,NLO>    iterative kappa-sigma clip about the MEAN with the population STD,
+//                       then the mean of the survivors.  Register-resident, float32 arithmetic
+//                       on pivot-shifted values with a rigorous error bound: a pixel whose
+//                       decision could differ from the float64 oracle is redone by the generic
+//                       routine, so rejection maps are identical.  Fed by a warp-granular
+//                       tensor-map TMA pipeline when the frames are equally spaced
+//                       (stack_meanclip.cuh), else by direct loads / cp.async.
+//   meanclip_coop<NBL,P> the same algorithm for 100 < N <= 512: P lanes share a pixel, P warps
+//                       share a 128B-swizzled TMA tile (stack_meanclip_coop.cuh);
+//                       meanclip_split (cp.async, 512 < N <= 1024), meanclip_smem (pointer tables).
+//   sorted<NB,MODE>     register-resident Batcher merge-exchange network (N <= 200) with
+//                       mixed ALU/FMA-pipe comparators: plain median (MODE_MED), or the
+//                       reference's ApMasterCal setting -- one median/MAD clip pass then the
+//                       mean (MODE_MEDMAD1) -- with the sorted column parked in shared memory
+//                       for the data-dependent MAD selection (stack_sorted.cuh).
 //   A pixel holding NaN/inf samples leaves the fast kernels for the generic
 //   routine, which owns the reference's non-finite semantics.
 #pragma once
