@@ -235,7 +235,10 @@ class ApMasterCal(ApBase):
         res = self.combine_frames(frames)
         first = self._files.files_filtered(include_path=True)[0]
         hdr = fitsio.read_header(first, 0).copy()
-        for kw in ("UT", "TIME-OBS", "SWOWNER", "SWCREATE", "SBSTDVER", "BZERO", "BSCALE", "PEDESTAL"):
+        # PEDESTAL stays, as in the reference: ccdproc.combine never applies it to the frames and keeps the
+        # first file's header, and ApCalibrate._read_fits (core/ApCalibrate.py:318-326) then removes the
+        # pedestal from the master exactly as it does from a raw frame
+        for kw in ("UT", "TIME-OBS", "SWOWNER", "SWCREATE", "SBSTDVER", "BZERO", "BSCALE"):
             if kw in hdr:
                 del hdr[kw]
         hdr["NCOMBINE"] = (nfiles, "Number of frames combined")

@@ -578,8 +578,13 @@ stack_meanclip_tmap_kernel(const __grid_constant__ CUtensorMap tmap, const __gri
         const int next = tile + nwarps;
         // re-arm the stage once the sums (which depend on every staged sample of every lane of
         // this warp instruction stream) exist: the predicate below carries that dependence
+        // (every lane's LDS reads of the stage are ordered before the async-proxy write: converge first)
         auto rearm = [&](float s2) {
-            if (lane == 0 && next < tile_end && s2 != -1.f) issue(next);
+            __syncwarp();
+            if (lane == 0 && next < tile_end && s2 != -1.f) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(next);
+            }
             __syncwarp();
         };
         meanclip_pixel<NB, NLO, SYM>(y, fp, a, (int64_t)(uint32_t)(pix0 + tile * WT + lane), rearm);

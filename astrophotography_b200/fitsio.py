@@ -18,7 +18,7 @@ from collections import OrderedDict
 
 import numpy as np
 
-try:                                    # pragma: no cover - not available offline
+try:
     from astropy.io import fits as _afits
     HAVE_ASTROPY = True
 except Exception:                       # noqa: BLE001
@@ -46,6 +46,7 @@ class Header:
     def __init__(self, cards=None):
         self._cards = OrderedDict()
         self.history = []
+        self.comment_cards = []
         if cards:
             for k, v in (cards.items() if hasattr(cards, "items") else cards):
                 self[k] = v
@@ -60,6 +61,9 @@ class Header:
         key = str(key).upper()
         if key == "HISTORY":
             self.history.append(str(value))
+            return
+        if key == "COMMENT":
+            self.comment_cards.append(str(value))
             return
         if isinstance(value, tuple):
             val, com = (value + ("",))[:2]
@@ -93,6 +97,7 @@ class Header:
         h = Header()
         h._cards = OrderedDict(self._cards)
         h.history = list(self.history)
+        h.comment_cards = list(self.comment_cards)
         return h
 
 
@@ -141,6 +146,7 @@ def _split_value_comment(body):
 
 def _read_header_block(f):
     hdr = Header()
+    last_str_key = None
     while True:
         block = f.read(BLOCK)
         if len(block) < BLOCK:
@@ -154,10 +160,26 @@ def _read_header_block(f):
                 break
             if key == "HISTORY":
                 hdr.history.append(card[8:].rstrip())
+            elif key == "COMMENT":
+                hdr.comment_cards.append(card[8:].rstrip())
+            elif key == "CONTINUE" and last_str_key is not None:
+                # long-string convention: the previous value ended in '&'
+                val, com = _split_value_comment(card[8:])
+                prev, pcom = hdr._cards[last_str_key]
+                more = _parse_value(val)
+                joined = (prev[:-1] if prev.endswith("&") else prev) + (more if isinstance(more, str) else "")
+                hdr._cards[last_str_key] = (joined, pcom or com)
+                if not joined.endswith("&"):
+                    last_str_key = None
             elif key and card[8:10] == "= ":
                 val, com = _split_value_comment(card[10:])
-                hdr._cards[key] = (_parse_value(val), com)
+                pv = _parse_value(val)
+                hdr._cards[key] = (pv, com)
+                last_str_key = key if isinstance(pv, str) and pv.endswith("&") else None
         if done:
+            for k, (v, c) in list(hdr._cards.items()):
+                if isinstance(v, str) and v.endswith("&"):
+                    hdr._cards[k] = (v[:-1], c)
             return hdr
 
 
@@ -205,19 +227,57 @@ def _fmt_value(val):
     if isinstance(val, (int, np.integer)):
         return f"{int(val):>20d}"
     if isinstance(val, (float, np.floating)):
+        if not np.isfinite(val):
+            # FITS has no NaN / inf tokens: written as a string (what astropy's 'silentfix' would leave readable)
+            return f"'{str(float(val)).upper():<8}'"
         s = repr(float(val)).upper()
-        if "E" not in s and "." not in s and "N" not in s:
+        if "E" not in s and "." not in s:
             s += ".0"
         return f"{s:>20}"
     s = str(val).replace("'", "''")
     return f"'{s:<8}'"
 
 
-def _card(key, val, com=""):
-    body = f"{key:<8}= {_fmt_value(val)}"
+def _string_cards(key, val, com=""):
+    """A string value that does not fit one card: OGIP long-string convention
+    (value pieces ending in '&' + CONTINUE cards), as astropy writes them."""
+    s = str(val).replace("'", "''")
+    pieces = []
+    while len(s) > 67:
+        cut = 67
+        if s[cut - 1] == "'" and (len(s[:cut]) - len(s[:cut].rstrip("'"))) % 2 == 1:
+            cut -= 1                    # do not split an escaped quote pair
+        pieces.append(s[:cut])
+        s = s[cut:]
+    pieces.append(s)
+    cards = []
+    for i, piece in enumerate(pieces):
+        last = i == len(pieces) - 1
+        text = f"'{piece}{'' if last else '&'}'"
+        body = (f"{key:<8}= " if i == 0 else "CONTINUE  ") + text
+        if last and com and len(body) + 3 + len(com) <= 80:
+            body += f" / {com}"
+        cards.append(body.ljust(80))
+    return cards
+
+
+def _cards_for(key, val, com=""):
+    """One or more 80-character cards for ``key = val / com``."""
+    if val is None:
+        return [f"{key:<8}=".ljust(80)[:80]]
+    fv = _fmt_value(val)
+    if fv.startswith("'") and len(fv) > 70:
+        return _string_cards(key, val, com)
+    body = f"{key:<8}= {fv}"
     if com:
-        body += f" / {com}"
-    return body[:80].ljust(80)
+        room = 80 - len(body) - 3
+        if room > 0:
+            body += f" / {com[:room]}"
+    return [body.ljust(80)]
+
+
+def _card(key, val, com=""):
+    return _cards_for(key, val, com)[0]
 
 
 def _encode_hdu(data, hdr, primary, extname=None):
@@ -259,9 +319,13 @@ def _encode_hdu(data, hdr, primary, extname=None):
         for key in hdr.keys():
             if key in _STRUCTURAL or (not primary and key == "EXTNAME"):
                 continue
-            cards.append(_card(key, hdr[key], hdr.comments[key]))
+            cards.extend(_cards_for(key, hdr[key], hdr.comments[key]))
+        for line in getattr(hdr, "comment_cards", []):
+            cards.append(("COMMENT " + str(line))[:80].ljust(80))
         for line in getattr(hdr, "history", []):
-            cards.append(("HISTORY " + str(line))[:80].ljust(80))
+            text = str(line)
+            for i in range(0, max(len(text), 1), 72):       # long HISTORY text wraps over several cards
+                cards.append(("HISTORY " + text[i:i + 72]).ljust(80))
     cards.append("END".ljust(80))
     head = "".join(cards).encode("ascii", "replace")
     head += b" " * (-len(head) % BLOCK)
@@ -275,20 +339,32 @@ def _encode_hdu(data, hdr, primary, extname=None):
 def read_image(path, ext=0):
     """Return ``(data, header)`` of image HDU ``ext`` (``uint=True`` semantics:
     BITPIX 16 with BZERO 32768 comes back as uint16)."""
-    if HAVE_ASTROPY:                    # pragma: no cover
+    if HAVE_ASTROPY:
         with _afits.open(path, uint=True, do_not_scale_image_data=False) as hl:
-            return np.asarray(hl[ext].data), hl[ext].header.copy()
+            data = np.asarray(hl[ext].data)
+            # FITS is big-endian and astropy keeps it that way ('>f4', '>i2'): torch.from_numpy refuses
+            # non-native byte order, so normalise once here
+            if data.dtype.byteorder not in ("=", "|"):
+                data = data.astype(data.dtype.newbyteorder("="))
+            return data, hl[ext].header.copy()
     return _mini_read(str(path), ext)
 
 
+def header_history(hdr):
+    """The HISTORY lines of a header as a list of str (astropy: ``hdr['HISTORY']``; stand-in: ``.history``)."""
+    if hasattr(hdr, "history"):
+        return list(hdr.history)
+    return [str(h) for h in hdr["HISTORY"]] if "HISTORY" in hdr else []
+
+
 def read_header(path, ext=0):
-    if HAVE_ASTROPY:                    # pragma: no cover
+    if HAVE_ASTROPY:
         return _afits.getheader(path, ext)
     return _mini_read(str(path), ext, header_only=True)[1]
 
 
 def new_header(cards=None):
-    if HAVE_ASTROPY:                    # pragma: no cover
+    if HAVE_ASTROPY:
         h = _afits.Header()
         for k, v in (cards or {}).items():
             h[k] = v
@@ -301,7 +377,7 @@ def write_image(path, data, header=None, extensions=(), overwrite=True):
     path = str(path)
     if os.path.exists(path) and not overwrite:
         raise OSError(f"{path} exists")
-    if HAVE_ASTROPY:                    # pragma: no cover
+    if HAVE_ASTROPY:
         hdus = [_afits.PrimaryHDU(data=data, header=header)]
         for name, d in extensions:
             hdus.append(_afits.ImageHDU(data=d, name=name))

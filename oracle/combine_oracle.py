@@ -68,8 +68,31 @@ def _mad_std0(a):
     return MAD_TO_STD * _nanmedian0(np.abs(a - med))
 
 
+ORDERS = ("bounds", "deviation")
+
+
+def _rejected(data, c, s, k_lo, k_hi, order):
+    """The clip decision in one of the two published operation orders.
+
+    ``bounds``     astropy.stats.sigma_clip (what ccdproc >= 2.4 delegates to):
+                   ``lo = c - s*k_lo; hi = c + s*k_hi; reject x < lo or x > hi``.
+    ``deviation``  ccdproc <= 2.3 ``Combiner.sigma_clipping`` (and the callable-function path):
+                   ``reject (x - c) < -k_lo*s or (x - c) > k_hi*s``.
+    The two differ only where a sample sits within an ulp or two of a clip bound
+    (``boundary_ties``); SURVEY.md section 7 item 1(b)."""
+    with np.errstate(invalid="ignore"):
+        if order == "bounds":
+            lo = c - s * k_lo
+            hi = c + s * k_hi
+            return (data < lo) | (data > hi)
+        if order == "deviation":
+            d = data - c
+            return (d < -k_lo * s) | (d > k_hi * s)
+    raise ValueError(order)
+
+
 def sigma_clip_stack(stack, k_lo=5.0, k_hi=5.0, maxiters=1,
-                     cen="median", dev="mad_std"):
+                     cen="median", dev="mad_std", order="bounds"):
     """Per-pixel sigma clipping along axis 0 (astropy.stats.sigma_clip semantics).
 
     Returns the float64 (N,H,W) array with rejected entries set to NaN.
@@ -89,10 +112,7 @@ def sigma_clip_stack(stack, k_lo=5.0, k_hi=5.0, maxiters=1,
         it += 1
         c = cenf(data)
         s = devf(data)
-        lo = c - s * k_lo
-        hi = c + s * k_hi
-        with np.errstate(invalid="ignore"):
-            rej = (data < lo) | (data > hi)
+        rej = _rejected(data, c, s, k_lo, k_hi, order)
         if not rej.any():
             break
         data[rej] = np.nan
@@ -100,7 +120,7 @@ def sigma_clip_stack(stack, k_lo=5.0, k_hi=5.0, maxiters=1,
 
 
 def combine(stack, method="average", k_lo=5.0, k_hi=5.0, maxiters=1,
-            cen="median", dev="mad_std", want_uncert=True):
+            cen="median", dev="mad_std", want_uncert=True, order="bounds"):
     """Restatement of ``ccdproc.combine`` on an in-memory (N,H,W) stack.
 
     Returns a dict: ``data`` (float64 H,W), ``nrej`` (int, number of the N
@@ -111,7 +131,7 @@ def combine(stack, method="average", k_lo=5.0, k_hi=5.0, maxiters=1,
         raise ValueError(method)
     stack = np.asarray(stack)
     n = stack.shape[0]
-    kept = sigma_clip_stack(stack, k_lo, k_hi, maxiters, cen, dev)
+    kept = sigma_clip_stack(stack, k_lo, k_hi, maxiters, cen, dev, order)
     nkept = np.sum(~np.isnan(kept), axis=0)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore", RuntimeWarning)
@@ -132,6 +152,18 @@ def combine(stack, method="average", k_lo=5.0, k_hi=5.0, maxiters=1,
                 u = np.nanstd(kept, axis=0)
             out["uncert"] = u / np.sqrt(nkept)
     return out
+
+
+def order_census(stack, k_lo, k_hi, maxiters, cen, dev):
+    """How the two operation orders relate on this stack: number of pixels, of pixels whose
+    rejection count differs between the orders, of ``boundary_ties`` pixels, and whether every
+    disagreement is a boundary tie (it must be)."""
+    a = combine(stack, "average", k_lo, k_hi, maxiters, cen, dev, want_uncert=False, order="bounds")["nrej"]
+    b = combine(stack, "average", k_lo, k_hi, maxiters, cen, dev, want_uncert=False, order="deviation")["nrej"]
+    ties = boundary_ties(stack, k_lo, k_hi, maxiters, cen, dev)
+    diff = a != b
+    return {"pixels": int(a.size), "orders_differ": int(diff.sum()), "boundary_ties": int(ties.sum()),
+            "differences_are_ties": bool(np.all(ties[diff]))}
 
 
 def boundary_ties(stack, k_lo, k_hi, maxiters, cen, dev, rel=1e-12):

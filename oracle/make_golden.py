@@ -208,14 +208,56 @@ def mint_combine_kat():
     print("combine_kat.npz")
 
 
+ORDER_CASES = {
+    # name: (generator, N, shape, seed, k_lo, k_hi, maxiters, cen, dev)
+    "dark30_apmastercal": ("dark", 30, (64, 96), 0, 5.0, 5.0, 1, "median", "mad_std"),
+    "dark30q_apmastercal": ("darkq", 30, (64, 96), 0, 5.0, 5.0, 1, "median", "mad_std"),
+    "dark100_kappa3": ("dark", 100, (32, 96), 0, 3.0, 3.0, 5, "mean", "std"),
+    "dark100q_kappa3": ("darkq", 100, (32, 96), 0, 3.0, 3.0, 5, "mean", "std"),
+    "dark200q_kappa3": ("darkq", 200, (16, 96), 0, 3.0, 3.0, 5, "mean", "std"),
+    "dark30q_astropy_default": ("darkq", 30, (64, 96), 0, 3.0, 3.0, 5, "median", "std"),
+    "tenths6_k1_mean_std": ("tenths", 6, (200, 200), 1, 1.0, 1.0, 1, "mean", "std"),
+    "tenths6_k1p5_mean_std_3it": ("tenths", 6, (200, 200), 2, 1.5, 1.5, 3, "mean", "std"),
+    "tenths8_k1_medmad": ("tenths", 8, (200, 200), 3, 1.0, 1.0, 1, "median", "mad_std"),
+}
+
+
+def order_case_stack(name):
+    """The seeded stack of one ORDER_CASES entry (the GPU tests rebuild it with the same call)."""
+    gen, n, shape, seed, *_ = ORDER_CASES[name]
+    if gen in ("dark", "darkq"):
+        return synth.dark_stack(n, shape, exptime=300.0, quantise=(gen == "darkq"))
+    rng = np.random.default_rng(seed)
+    # multiples of 0.1 in float32: sample, centre and k*std all land on few-digit decimals, so
+    # samples sit exactly on clip bounds and the two operation orders round differently
+    return rng.integers(0, 12, (n,) + tuple(shape)).astype(np.float32) * np.float32(0.1)
+
+
+def mint_order_census():
+    """Tie census per configuration: where ``lo = c - k*s; x < lo`` (astropy / ccdproc >= 2.4) and
+    ``x - c < -k*s`` (ccdproc <= 2.3) disagree.  Every disagreement must be a boundary tie."""
+    from oracle import combine_oracle as C
+    out = {}
+    for name, (_gen, _n, _shape, _seed, k_lo, k_hi, maxiters, cen, dev) in ORDER_CASES.items():
+        out[name] = C.order_census(order_case_stack(name), k_lo, k_hi, maxiters, cen, dev)
+        assert out[name]["differences_are_ties"], name
+    with open(os.path.join(GOLD, "combine_order_census.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    print("combine_order_census.json", {k: (v["orders_differ"], v["boundary_ties"]) for k, v in out.items()})
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    if "--order-census" in sys.argv:
+        mint_order_census()
+        return
     if not ref_exec.reference_available():
         raise SystemExit("needs /root/reference (authoring container)")
     mint_calibrate()
     mint_badpix()
     mint_findbadpix()
     mint_combine_kat()
+    mint_order_census()
 
 
 if __name__ == "__main__":

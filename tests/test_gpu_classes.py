@@ -43,7 +43,7 @@ def test_apcalibrate_files_match_reference_goldens(cuda, golden_dir, tmp_path):
         if usemask:
             assert (hdr["BPIXNBAD"], hdr["BPIXNFIX"], hdr["BPIXNREM"]) == (nbad, nfix, nrem)
             assert hdr["BPIXFILE"] == "mask.fits" and hdr["BPIXDPIX"] == dp and hdr["BPIX_MIN"] == 4
-        assert any("Processed by ApCalibrate" in ln for ln in hdr.history)
+        assert any("Processed by ApCalibrate" in ln for ln in fitsio.header_history(hdr))
 
 
 def test_apcalibrate_errors(cuda, tmp_path):
@@ -170,6 +170,42 @@ def test_apmastercal_make_master(cuda, tmp_path):
     mc2.make_master(str(tmp_path / "median.fits"))
     med, _ = fitsio.read_image(tmp_path / "median.fits", 0)
     assert med.dtype == np.float32 and np.array_equal(med, np.median(st.astype(np.float64), axis=0).astype(np.float32))
+
+
+def test_master_keeps_pedestal_and_apcalibrate_removes_it(cuda, tmp_path):
+    """MaximDL-style frames carry PEDESTAL=-100.  Like ccdproc.combine the master keeps the keyword (the
+    frames are combined as stored) and ApCalibrate._read_fits removes the pedestal from the master bias /
+    dark exactly as from the raw frame (reference core/ApCalibrate.py:318-326)."""
+    import astrophotography_b200 as ap
+    from astrophotography_b200 import ApMasterCal, fitsio, synth
+    from oracle import calibrate_oracle as co, combine_oracle as C
+    shape, n, ped = (32, 48), 7, -100
+    masters = {}
+    for kind, exptime, typ in (("bias", 0.0, "Bias Frame"), ("dark", 600.0, "Dark Frame")):
+        dd = tmp_path / kind
+        dd.mkdir()
+        st = synth.dark_stack(n, shape, exptime=exptime, quantise=True)
+        for k in range(n):
+            fitsio.write_image(dd / f"{kind}{k}.fits", st[k].astype(np.uint16),
+                               fitsio.new_header({"IMAGETYP": typ, "EXPTIME": exptime, "SET-TEMP": -20.0, "CCD-TEMP": -20.0,
+                                                  "TELESCOP": "T5", "PEDESTAL": ped}))
+        out = str(tmp_path / f"master_{kind}.fits")
+        ApMasterCal(str(dd), "master*", "T5", 0.5, "ERROR", out_dtype="float32").make_master(out)
+        data, hdr = fitsio.read_image(out, 0)
+        assert hdr["PEDESTAL"] == ped                                   # kept, not applied
+        exp = C.combine(st, "average", 5, 5, 1, "median", "mad_std")["data"].astype(np.float32)
+        assert np.array_equal(data, exp)
+        masters[kind] = (out, exp)
+    raw = synth.science_frame(shape, nstars=3)
+    rawf = str(tmp_path / "raw.fits")
+    fitsio.write_image(rawf, raw, fitsio.new_header({"EXPTIME": 300.0, "PEDESTAL": ped}))
+    cal = ap.ApCalibrate(masters["bias"][0], masters["dark"][0], None, None, "ERROR", True)
+    cal.calibrate(rawf, str(tmp_path / "cal.fits"), 2, None, False)
+    got, h = fitsio.read_image(tmp_path / "cal.fits", 0)
+    bias = masters["bias"][1] + np.float32(ped)
+    dark = masters["dark"][1] + np.float32(ped)
+    exp = co.calibrate(co.read_convert(raw, float(ped)), bias, dark, 300.0 / 600.0, None, True)
+    assert bits_equal(got, exp) and "PEDESTAL" not in h
 
 
 def test_cli_mains_end_to_end(cuda, golden_dir, tmp_path):

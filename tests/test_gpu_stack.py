@@ -368,3 +368,53 @@ def test_stack_errors(cuda):
         kernels.stack_reduce(a, row0=3, nrows=2)
     with pytest.raises(RuntimeError):
         kernels.stack_reduce(torch.zeros((0, 4, 4), device="cuda"))
+
+
+# ---------------------------------------------------------------- the two published operation orders
+def _order_case_names():
+    from oracle import make_golden as G
+    return sorted(G.ORDER_CASES)
+
+
+@pytest.mark.parametrize("name", _order_case_names())
+def test_nrej_equals_both_operation_orders_off_ties(cuda, golden_dir, name):
+    """Rejection maps equal the astropy order (``x < c - k*s``) everywhere and the ccdproc <= 2.3 order
+    (``x - c < -k*s``) everywhere except on boundary-tie pixels; the tie census is a committed golden."""
+    import json
+    from oracle import combine_oracle as C, make_golden as G
+    torch = cuda
+    _gen, _n, _shape, _seed, k_lo, k_hi, maxiters, cen, dev = G.ORDER_CASES[name]
+    st = G.order_case_stack(name)
+    with open(os.path.join(golden_dir, "combine_order_census.json")) as f:
+        census = json.load(f)[name]
+    assert C.order_census(st, k_lo, k_hi, maxiters, cen, dev) == census
+    a = C.combine(st, "average", k_lo, k_hi, maxiters, cen, dev, want_uncert=False, order="bounds")
+    b = C.combine(st, "average", k_lo, k_hi, maxiters, cen, dev, want_uncert=False, order="deviation")
+    ties = C.boundary_ties(st, k_lo, k_hi, maxiters, cen, dev)
+    for force in (False, True):
+        got = _run(torch, st, method="average", k_lo=k_lo, k_hi=k_hi, maxiters=maxiters, cen=cen, dev=dev,
+                   force_generic=force)
+        nrej = got["nrej"].astype(np.int64)
+        assert np.array_equal(nrej, a["nrej"]), (name, force)
+        assert np.array_equal(nrej[~ties], b["nrej"][~ties]), (name, force)
+        _assert_close_data(got["data"], a["data"], RTOL32, 1.0)
+
+
+def test_real_ccdproc_cross_check_on_this_box(cuda):
+    """Attempted on the GPU box too (the authoring container has no ccdproc/astropy): when the real
+    library is importable, the oracle AND the CUDA path are compared with it."""
+    ccdproc = pytest.importorskip("ccdproc")
+    from astropy.nddata import CCDData
+    from astropy.stats import mad_std
+    from oracle import combine_oracle as C
+    torch = cuda
+    rng = np.random.default_rng(9)
+    st = rng.normal(1000, 12, (12, 16, 16)).astype(np.float32)
+    st[2, 3, 3] += 5000
+    ccds = [CCDData(f, unit="adu") for f in st]
+    ref = ccdproc.combine(ccds, method="average", sigma_clip=True, sigma_clip_low_thresh=5, sigma_clip_high_thresh=5,
+                          sigma_clip_func=np.ma.median, sigma_clip_dev_func=mad_std)
+    mine = C.combine(st, "average", 5, 5, 1, "median", "mad_std")
+    assert np.allclose(np.asarray(ref.data), mine["data"], rtol=1e-12)
+    got = _run(torch, st, out_f64=True)
+    assert np.allclose(got["data"], np.asarray(ref.data), rtol=1e-12)

@@ -108,6 +108,162 @@ def test_fits_roundtrip(tmp_path, dtype):
     assert fitsio.read_header(path, 0)["SET-TEMP"] == -20.0
 
 
+def test_fits_long_strings_comments_and_nonfinite(tmp_path):
+    """Cards the reference's outputs really carry: DATAFILE / BIASFILE / IFILEnnn hold long paths, COMMENT
+    cards must survive a header copy, NaN / inf values must not produce invalid tokens."""
+    long_path = "/data/iTelescope/T05/2024-01-30/calibration/" + "very_long_directory_name/" * 3 + "master_dark_-20C_900s.fits"
+    quoted = "it's " * 20
+    hdr = fitsio.new_header({"DATAFILE": (long_path, "Data file used to generate mask"), "OBSERVER": quoted,
+                             "SHORT": ("abc", "a comment that is far too long to fit on the card " * 3),
+                             "BADVAL": float("nan"), "INFVAL": float("inf"), "AFTER": 7})
+    hdr["COMMENT"] = "FITS (Flexible Image Transport System) format"
+    hdr["HISTORY"] = "x" * 150
+    path = tmp_path / "long.fits"
+    fitsio.write_image(path, np.zeros((3, 4), np.float32), hdr)
+    raw = open(path, "rb").read()
+    assert len(raw) % 2880 == 0
+    head = raw[: raw.index(b"END" + b" " * 77) + 80].decode("ascii")
+    assert len(head) % 80 == 0
+    for i in range(0, len(head), 80):                       # every string card is closed
+        card = head[i:i + 80]
+        if card[:8].strip() in ("DATAFILE", "OBSERVER", "CONTINUE", "SHORT"):
+            val = card[10:] if card[8:10] == "= " else card[8:]
+            assert fitsio._split_value_comment(val)[0].strip().endswith("'"), card
+    _, h2 = fitsio.read_image(path, 0)
+    assert h2["DATAFILE"] == long_path and h2["OBSERVER"] == quoted.rstrip() and h2["SHORT"] == "abc" and h2["AFTER"] == 7
+    assert h2["BADVAL"] == "NAN" and h2["INFVAL"] == "INF"
+    assert h2.comment_cards == ["FITS (Flexible Image Transport System) format"]
+    assert "".join(fitsio.header_history(h2)) == "x" * 150
+    c = h2.copy()
+    assert c.comment_cards == h2.comment_cards
+
+
+def _fake_astropy_modules():
+    """A stand-in for ``astropy.io.fits`` with the properties that matter at the seam: big-endian data arrays,
+    a Header without ``.history`` whose ``['HISTORY']`` is a list, HDU objects and ``HDUList.writeto``."""
+    import types
+
+    class FakeHeader(dict):
+        def __init__(self):
+            super().__init__()
+            self._com, self._hist = {}, []
+        def __setitem__(self, k, v):
+            k = k.upper()
+            if k == "HISTORY":
+                self._hist.append(str(v))
+                return
+            if isinstance(v, tuple):
+                self._com[k] = v[1] if len(v) > 1 else ""
+                v = v[0]
+            super().__setitem__(k, v)
+        def __getitem__(self, k):
+            return list(self._hist) if k.upper() == "HISTORY" else super().__getitem__(k.upper())
+        def __contains__(self, k):
+            return (k.upper() == "HISTORY" and bool(self._hist)) or super().__contains__(k.upper())
+        def __delitem__(self, k):
+            super().__delitem__(k.upper())
+        def get(self, k, d=None):
+            return self[k] if k in self else d
+        @property
+        def comments(self):
+            return {k: self._com.get(k, "") for k in self.keys()}
+        def copy(self):
+            h = FakeHeader()
+            for k in self.keys():
+                h[k] = (dict.__getitem__(self, k), self._com.get(k, ""))
+            h._hist = list(self._hist)
+            return h
+
+    def to_fake(h):
+        f = FakeHeader()
+        for k in h.keys():
+            f[k] = (h[k], h.comments[k])
+        for ln in h.history:
+            f["HISTORY"] = ln
+        return f
+
+    def from_fake(f):
+        h = fitsio.Header()
+        for k in f.keys():
+            h[k] = (dict.__getitem__(f, k), f._com.get(k, ""))
+        for ln in f._hist:
+            h["HISTORY"] = ln
+        return h
+
+    class HDU:
+        def __init__(self, data=None, header=None, name=None):
+            self.data, self.header, self.name = data, header if header is not None else FakeHeader(), name
+    class HDUList(list):
+        def writeto(self, path, output_verify="exception", overwrite=False):
+            blob = b""
+            for i, hdu in enumerate(self):
+                blob += fitsio._encode_hdu(hdu.data, from_fake(hdu.header), i == 0, extname=hdu.name)
+            with open(path, "wb") as f:
+                f.write(blob)
+        def __enter__(self):
+            return self
+        def __exit__(self, *a):
+            return False
+
+    def fits_open(path, uint=False, do_not_scale_image_data=False):
+        out = HDUList()
+        ext = 0
+        while True:
+            try:
+                data, hdr = fitsio._mini_read(str(path), ext)
+            except (OSError, KeyError):
+                break
+            if data is not None and data.dtype.itemsize > 1:
+                data = data.astype(data.dtype.newbyteorder(">"))     # astropy hands out big-endian arrays
+            out.append(HDU(data, to_fake(hdr)))
+            ext += 1
+        return out
+
+    fits = types.ModuleType("astropy.io.fits")
+    fits.open, fits.Header, fits.PrimaryHDU, fits.ImageHDU, fits.HDUList = fits_open, FakeHeader, HDU, HDU, HDUList
+    fits.getheader = lambda path, ext=0: fits_open(path)[ext].header
+    io = types.ModuleType("astropy.io")
+    io.fits = fits
+    top = types.ModuleType("astropy")
+    top.io = io
+    return {"astropy": top, "astropy.io": io, "astropy.io.fits": fits}
+
+
+def test_astropy_branch_of_the_seam_with_a_shim(tmp_path, monkeypatch):
+    """The ``HAVE_ASTROPY`` branches of fitsio (never reachable offline otherwise): native byte order out of
+    ``read_image``, HISTORY through ``header_history``, keyword round trip, extensions."""
+    import importlib
+    for name, mod in _fake_astropy_modules().items():
+        monkeypatch.setitem(sys.modules, name, mod)
+    try:
+        importlib.reload(fitsio)
+        assert fitsio.HAVE_ASTROPY
+        data = (np.arange(12 * 20).reshape(12, 20) * 3).astype(np.uint16)
+        hdr = fitsio.new_header({"EXPTIME": (300.0, "seconds"), "PEDESTAL": -100})
+        hdr["HISTORY"] = "made by the shim test"
+        path = tmp_path / "shim.fits"
+        fitsio.write_image(path, data, hdr, extensions=[("MASK", (data > 100).astype(np.int16)), ("UNCERT", data.astype(np.float64))])
+        back, h2 = fitsio.read_image(path, 0)
+        assert back.dtype == np.uint16 and back.dtype.isnative and np.array_equal(back, data)
+        assert h2["EXPTIME"] == 300.0 and h2["PEDESTAL"] == -100 and not hasattr(h2, "history")
+        assert fitsio.header_history(h2) == ["made by the shim test"]
+        m, _ = fitsio.read_image(path, 1)
+        u, _ = fitsio.read_image(path, 2)
+        assert m.dtype == np.int16 and m.dtype.isnative and u.dtype == np.float64 and u.dtype.isnative
+        import torch
+        torch.from_numpy(m)                      # what _mask_to_device does: must not raise on byte order
+        torch.from_numpy(u)
+        assert fitsio.read_header(path, 0)["EXPTIME"] == 300.0
+        hc = h2.copy()
+        del hc["PEDESTAL"]
+        hc["HISTORY"] = "second"
+        assert "PEDESTAL" not in hc and "PEDESTAL" in h2 and len(fitsio.header_history(hc)) == 2
+    finally:
+        monkeypatch.undo()
+        importlib.reload(fitsio)
+    assert not fitsio.HAVE_ASTROPY or "astropy" in sys.modules
+
+
 def test_header_mapping():
     h = fitsio.Header({"A": 1})
     h["b"] = (2, "two")

@@ -175,6 +175,23 @@ def test_sigma_clip_properties():
     assert abs(med - 100) < 2 and 3 < std < 7
 
 
+def test_two_operation_orders_differ_only_at_ties(golden_dir):
+    """``lo = c - k*s; x < lo`` (astropy, ccdproc >= 2.4) against
+    ``x - c < -k*s`` (ccdproc <= 2.3).  The committed census says how often they disagree per
+    configuration; every disagreement is a documented kappa-boundary tie."""
+    import json
+    from oracle import make_golden as G
+    with open(os.path.join(golden_dir, "combine_order_census.json")) as f:
+        census = json.load(f)
+    assert set(census) == set(G.ORDER_CASES)
+    assert census["tenths6_k1_mean_std"]["orders_differ"] > 0        # the orders are really different
+    for name in ("dark30q_apmastercal", "tenths6_k1_mean_std", "tenths8_k1_medmad", "dark30q_astropy_default"):
+        _gen, _n, _shape, _seed, k_lo, k_hi, maxiters, cen, dev = G.ORDER_CASES[name]
+        got = C.order_census(G.order_case_stack(name), k_lo, k_hi, maxiters, cen, dev)
+        assert got == census[name], name
+        assert got["differences_are_ties"]
+
+
 def test_against_real_ccdproc_if_present():
     ccdproc = pytest.importorskip("ccdproc")
     from astropy.nddata import CCDData
