@@ -26,6 +26,10 @@ SIGNATURES = {
         _c.POINTER(_P), _c.c_int, _c.c_int64, _c.c_int64, _c.c_int64, _c.c_int64, _c.c_int,
         _c.c_double, _c.c_double, _c.c_int, _c.c_int, _c.c_int,
         _P, _c.c_int, _P, _c.c_int, _P, _P, _c.c_int, _P]),
+    "apgpu_stack_reduce_u16": (_c.c_int, [
+        _c.POINTER(_P), _c.c_int, _c.c_int, _c.c_int64, _c.c_int64, _c.c_int64, _c.c_int64, _c.c_int,
+        _c.c_double, _c.c_double, _c.c_int, _c.c_int, _c.c_int,
+        _P, _c.c_int, _P, _c.c_int, _P, _P, _c.c_int, _P]),
     "apgpu_stack_kernel_name": (_c.c_char_p, [
         _c.c_int, _c.c_int, _c.c_double, _c.c_double, _c.c_int, _c.c_int, _c.c_int,
         _c.c_int, _c.c_int, _c.c_int]),

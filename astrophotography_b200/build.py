@@ -21,9 +21,47 @@ INCLUDE = os.path.join(ROOT, "include")
 BUILD_DIR = os.path.join(PKG_DIR, "_build")
 LIB_PATH = os.path.join(PKG_DIR, "libapgpu.so")
 
-SOURCES = ["stack_meanclip_coop_p8.cu", "stack_meanclip_coop_p4.cu", "stack_meanclip_coop_p2.cu", "stack_meanclip_split_p8.cu", "stack_meanclip_mid.cu", "stack_meanclip_hi.cu", "stack_meanclip_lo.cu", "stack_sorted_medmad1.cu",
-           "stack_sorted_med.cu", "stack_meanclip_smem.cu", "stack_generic.cu", "stack.cu",
-           "apgpu_core.cu", "calibrate.cu", "badpix.cu", "stats.cu"]
+SOURCES = ['stack_sorted_med_f32_p3.cu',
+           'stack_sorted_med_u16_p3.cu',
+           'stack_sorted_medmad1_f32_p3.cu',
+           'stack_sorted_medmad1_u16_p3.cu',
+           'stack_sorted_medunc_f32_p3.cu',
+           'stack_sorted_medunc_u16_p3.cu',
+           'stack_sorted_med_f32_p2.cu',
+           'stack_sorted_med_u16_p2.cu',
+           'stack_sorted_medmad1_f32_p2.cu',
+           'stack_sorted_medmad1_u16_p2.cu',
+           'stack_sorted_medunc_f32_p2.cu',
+           'stack_sorted_medunc_u16_p2.cu',
+           'stack_sorted_med_f32_p1.cu',
+           'stack_sorted_med_u16_p1.cu',
+           'stack_sorted_medmad1_f32_p1.cu',
+           'stack_sorted_medmad1_u16_p1.cu',
+           'stack_sorted_medunc_f32_p1.cu',
+           'stack_sorted_medunc_u16_p1.cu',
+           'stack_sorted_med_f32_p0.cu',
+           'stack_sorted_med_u16_p0.cu',
+           'stack_sorted_medmad1_f32_p0.cu',
+           'stack_sorted_medmad1_u16_p0.cu',
+           'stack_sorted_medunc_f32_p0.cu',
+           'stack_sorted_medunc_u16_p0.cu',
+           'stack_meanclip_coop_p8.cu',
+           'stack_meanclip_coop_p4.cu',
+           'stack_meanclip_coop_p2.cu',
+           'stack_meanclip_split_p8.cu',
+           'stack_meanclip_mid.cu',
+           'stack_meanclip_hi.cu',
+           'stack_meanclip_lo.cu',
+           'stack_meanclip_mid_u16.cu',
+           'stack_meanclip_hi_u16.cu',
+           'stack_meanclip_lo_u16.cu',
+           'stack_meanclip_smem.cu',
+           'stack_generic.cu',
+           'stack.cu',
+           'apgpu_core.cu',
+           'calibrate.cu',
+           'badpix.cu',
+           'stats.cu']
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

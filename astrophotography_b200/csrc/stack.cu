@@ -39,7 +39,8 @@ namespace apgpu_stack {
 // ---------------------------------------------------------------------------
 // host dispatch
 // ---------------------------------------------------------------------------
-enum Family { FAM_GENERIC = 0, FAM_MEANCLIP = 1, FAM_SORT_MED = 2, FAM_SORT_MEDMAD1 = 3, FAM_MEANCLIP_SMEM = 4 };
+enum Family { FAM_GENERIC = 0, FAM_MEANCLIP = 1, FAM_SORT_MED = 2, FAM_SORT_MEDMAD1 = 3, FAM_MEANCLIP_SMEM = 4,
+              FAM_SORT_MEDUNC = 5 };
 
 constexpr int MEANCLIP_SMEM_MAX_N = 4 * ((SMEM_MAX_BYTES / (TPB * 16)) & ~1);   // 452
 constexpr int MEANCLIP_REG_DEFAULT_MAX_N = 200;  // measured: the register kernel wins wherever it exists (bench.py variants)
@@ -50,6 +51,9 @@ const Bucket MEANCLIP_BUCKETS[] = {{8, 2}, {16, 8}, {24, 16}, {32, 24}, {48, 32}
 const Bucket SORT_BUCKETS[] = {{4, 0}, {8, 4}, {12, 8}, {16, 12}, {20, 16}, {24, 20}, {32, 24}, {40, 32},
                                {48, 40}, {56, 48}, {64, 56}, {72, 64}, {80, 72}, {90, 80}, {100, 90},
                                {112, 100}, {128, 112}, {160, 128}, {200, 160}};
+
+const Bucket SORT_BUCKETS_COARSE[] = {{4, 0}, {8, 4}, {16, 8}, {24, 16}, {32, 24}, {48, 32}, {64, 48}, {80, 64},
+                                      {100, 80}, {128, 100}, {160, 128}, {200, 160}};
 
 template <size_t K>
 const Bucket* find_bucket(const Bucket (&b)[K], int N) {
@@ -77,8 +81,10 @@ Family choose_family(int N, int method, double klo, double khi, int maxiters, in
         if (use_reg) { *bucket = rb; return FAM_MEANCLIP; }
         if (smem_ok) return FAM_MEANCLIP_SMEM;
     }
-    if (method == APGPU_METHOD_MEDIAN && maxiters == 0 && !want_uncert) {
-        if ((*bucket = find_bucket(SORT_BUCKETS, N))) return FAM_SORT_MED;
+    if (method == APGPU_METHOD_MEDIAN && maxiters == 0) {
+        // with an uncertainty plane (what ApMasterCal always asks for) the MAD of every pixel is needed:
+        // full network + parked column, like the median/MAD clip
+        if ((*bucket = find_bucket(SORT_BUCKETS, N))) return want_uncert ? FAM_SORT_MEDUNC : FAM_SORT_MED;
     }
     if (method == APGPU_METHOD_AVERAGE && maxiters == 1 && cen == APGPU_CEN_MEDIAN &&
         dev == APGPU_DEV_MAD_STD && N >= 2) {
@@ -111,7 +117,20 @@ int stack_dispatch_meanclip_split(const float* const* frames, const StackArgs& a
     return APGPU_ERR_UNSUPPORTED;
 }
 
-int stack_dispatch_meanclip(int nb, const float* const* frames, const StackArgs& a, cudaStream_t st, int flags) {
+template <int MODE, typename T>
+int stack_dispatch_sorted(int N, const T* const* frames, const StackArgs& a, cudaStream_t st) {
+    const Bucket* b = sorted_fine_buckets<MODE, T>() ? find_bucket(SORT_BUCKETS, N) : find_bucket(SORT_BUCKETS_COARSE, N);
+    if (!b) return APGPU_ERR_UNSUPPORTED;
+    switch (sorted_part_of(b->nb)) {
+        case 0: return dispatch_sorted_part<MODE, T, 0>(b->nb, frames, a, st);
+        case 1: return dispatch_sorted_part<MODE, T, 1>(b->nb, frames, a, st);
+        case 2: return dispatch_sorted_part<MODE, T, 2>(b->nb, frames, a, st);
+        default: return dispatch_sorted_part<MODE, T, 3>(b->nb, frames, a, st);
+    }
+}
+
+template <typename T>
+int stack_dispatch_meanclip(int nb, const T* const* frames, const StackArgs& a, cudaStream_t st, int flags) {
     if (nb <= 64) return stack_dispatch_meanclip_lo(nb, frames, a, st, flags);
     if (nb <= 128) return stack_dispatch_meanclip_mid(nb, frames, a, st, flags);
     return stack_dispatch_meanclip_hi(nb, frames, a, st, flags);
@@ -135,18 +154,18 @@ int stack_coop_box_rows_max() {
     }
     return v;
 }
-bool stack_is_cube(const float* const* frames, int N, int64_t npix_end) {
+bool stack_is_cube_bytes(const void* const* frames, int N, int64_t npix_end, int elem_bytes) {
     if (N < 2 || npix_end <= 0 || npix_end >= ((int64_t)1 << 31)) return false;
     const int64_t stride = (const char*)frames[1] - (const char*)frames[0];
-    if (stride < npix_end * (int64_t)sizeof(float) || stride % 16 != 0 || stride >= ((int64_t)1 << 40)) return false;
+    if (stride < npix_end * (int64_t)elem_bytes || stride % 16 != 0 || stride >= ((int64_t)1 << 40)) return false;
     if (!apgpu_aligned(frames[0], 16)) return false;
     for (int i = 2; i < N; ++i)
         if ((const char*)frames[i] - (const char*)frames[i - 1] != stride) return false;
     return true;
 }
 
-bool encode_stack_tensor_map(CUtensorMap* tmap, const float* base, uint64_t npix_end, int N,
-                             uint64_t stride_bytes, int box_pix, int box_rows, bool swizzle128) {
+bool encode_stack_tensor_map_bytes(CUtensorMap* tmap, const void* base, int elem_bytes, uint64_t npix_end, int N,
+                                   uint64_t stride_bytes, int box_pix, int box_rows, bool swizzle128) {
     // cuTensorMapEncodeTiled lives in the driver (libcuda): fetched through the runtime so that the
     // library keeps linking against cudart only
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -167,7 +186,8 @@ bool encode_stack_tensor_map(CUtensorMap* tmap, const float* base, uint64_t npix
     const cuuint64_t gstride[1] = {stride_bytes};
     const cuuint32_t box[2] = {(cuuint32_t)box_pix, (cuuint32_t)(box_rows > 0 ? box_rows : N)};
     const cuuint32_t estride[2] = {1, 1};
-    return encode(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estride,
+    return encode(tmap, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(base), gdim, gstride, box, estride,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -210,6 +230,7 @@ extern "C" const char* apgpu_stack_kernel_name(int N, int method, double k_lo, d
         case FAM_MEANCLIP_SMEM: snprintf(g_kname, sizeof(g_kname), "meanclip_smem"); break;
         case FAM_SORT_MED: snprintf(g_kname, sizeof(g_kname), "sorted_median<%d>", b->nb); break;
         case FAM_SORT_MEDMAD1: snprintf(g_kname, sizeof(g_kname), "sorted_medmad1<%d>", b->nb); break;
+        case FAM_SORT_MEDUNC: snprintf(g_kname, sizeof(g_kname), "sorted_median_mad<%d>", b->nb); break;
         default: snprintf(g_kname, sizeof(g_kname), "generic<%d>", N <= 32 ? 32 : (N <= 128 ? 128 : 1024)); break;
     }
     return g_kname;
@@ -217,13 +238,16 @@ extern "C" const char* apgpu_stack_kernel_name(int N, int method, double k_lo, d
 
 extern "C" int apgpu_stack_last_staging(void) { return g_last_staging; }
 
-extern "C" int apgpu_stack_reduce_f32(const float* const* frames, int N, int64_t H, int64_t W,
-                                      int64_t row0, int64_t nrows, int method,
-                                      double k_lo, double k_hi, int maxiters, int cen, int dev,
-                                      void* out_data, int out_is_f64,
-                                      void* out_nrej, int nrej_is_u16,
-                                      void* out_uncert, uint8_t* out_allmasked,
-                                      int flags, apgpu_stream_t stream) {
+namespace apgpu_stack {
+
+template <typename T>
+int stack_reduce_impl(const T* const* frames, int u16_format, int N, int64_t H, int64_t W,
+                      int64_t row0, int64_t nrows, int method,
+                      double k_lo, double k_hi, int maxiters, int cen, int dev,
+                      void* out_data, int out_is_f64,
+                      void* out_nrej, int nrej_is_u16,
+                      void* out_uncert, uint8_t* out_allmasked,
+                      int flags, apgpu_stream_t stream) {
     APGPU_REQUIRE(frames && out_data, "stack_reduce: null frames/out pointer");
     APGPU_REQUIRE(N >= 1 && N <= APGPU_STACK_MAX_FRAMES, "stack_reduce: N=%d outside 1..%d", N, APGPU_STACK_MAX_FRAMES);
     APGPU_REQUIRE(H > 0 && W > 0 && row0 >= 0 && nrows >= 0 && row0 + nrows <= H,
@@ -235,7 +259,11 @@ extern "C" int apgpu_stack_reduce_f32(const float* const* frames, int N, int64_t
     APGPU_REQUIRE(dev == APGPU_DEV_STD || dev == APGPU_DEV_MAD_STD, "stack_reduce: bad dev %d", dev);
     APGPU_REQUIRE(maxiters == 0 || (k_lo == k_lo && k_hi == k_hi), "stack_reduce: NaN clip threshold");
     APGPU_REQUIRE(!out_nrej || nrej_is_u16 || N <= 255, "stack_reduce: uint8 rejection map needs N <= 255 (N=%d)", N);
+    APGPU_REQUIRE(u16_format == APGPU_U16_NATIVE || u16_format == APGPU_U16_FITS_BZERO,
+                  "stack_reduce: bad uint16 sample format %d", u16_format);
     for (int i = 0; i < N; ++i) APGPU_REQUIRE(frames[i], "stack_reduce: frame %d is null", i);
+    for (int i = 0; i < N; ++i)
+        APGPU_REQUIRE(apgpu_aligned(frames[i], sizeof(T)), "stack_reduce: frame %d is not aligned to its sample size", i);
     if (nrows == 0) return APGPU_OK;
 
     StackArgs a;
@@ -246,33 +274,67 @@ extern "C" int apgpu_stack_reduce_f32(const float* const* frames, int N, int64_t
     a.nrej = out_nrej; a.nrej_u16 = nrej_is_u16;
     a.uncert = out_uncert; a.allmasked = out_allmasked;
     a.one = 1; a.minus_one = -1; a.tiles_per_warp = 0; a.box_rows = 0; a.nchunks = 0;
+    a.u16_sel = u16_format == APGPU_U16_FITS_BZERO ? 0x7601u : 0x7610u;
+    a.u16_xor = u16_format == APGPU_U16_FITS_BZERO ? 0x8000u : 0u;
+    a.sample_bias = sample_bias_of<T>();
+    for (int i = 0; i < MEANCLIP_MAX_TAIL; ++i) a.tailmask[i] = 0.f;
     cudaStream_t st = (cudaStream_t)stream;
     g_last_staging = -1;
 
     // long stacks on equally spaced frames: the lane-split tensor-map kernels take every full warp tile,
-    // whatever follows only sees the (< 32-pixel) tail
-    if (N > 100 && meanclip_eligible(N, method, k_lo, k_hi, maxiters, cen, dev, flags)) {
-        int64_t done = 0;
-        const int rc = stack_dispatch_meanclip_split(frames, a, st, flags, &done);
-        if (rc != APGPU_OK && rc != APGPU_ERR_UNSUPPORTED) return rc;
-        if (rc == APGPU_OK) {
-            a.pix0 += done;
-            a.npix -= done;
-            if (a.npix == 0) return APGPU_OK;
+    // whatever follows only sees the (< 32-pixel) tail  (float32 frames; uint16 frames use the register
+    // kernels up to N = 200)
+    if constexpr (sizeof(T) == sizeof(float)) {
+        if (N > 100 && meanclip_eligible(N, method, k_lo, k_hi, maxiters, cen, dev, flags)) {
+            int64_t done = 0;
+            const int rc = stack_dispatch_meanclip_split(frames, a, st, flags, &done);
+            if (rc != APGPU_OK && rc != APGPU_ERR_UNSUPPORTED) return rc;
+            if (rc == APGPU_OK) {
+                a.pix0 += done;
+                a.npix -= done;
+                if (a.npix == 0) return APGPU_OK;
+            }
         }
     }
     const int staging_so_far = g_last_staging;
 
     const Bucket* b = nullptr;
     Family f = choose_family(N, method, k_lo, k_hi, maxiters, cen, dev, out_uncert != nullptr, flags, &b);
+    if (sizeof(T) != sizeof(float) && f == FAM_MEANCLIP_SMEM) f = FAM_GENERIC;
     struct Restore { int v; ~Restore() { if (v >= 0) g_last_staging = v; } } restore{staging_so_far};
     switch (f) {
         case FAM_MEANCLIP: return stack_dispatch_meanclip(b->nb, frames, a, st, flags);
         case FAM_MEANCLIP_SMEM:
-            return stack_launch_meanclip_smem(frames, a, st);
-        case FAM_SORT_MED: return stack_dispatch_sorted_med(b->nb, frames, a, st);
-        case FAM_SORT_MEDMAD1: return stack_dispatch_sorted_medmad1(b->nb, frames, a, st);
+            if constexpr (sizeof(T) == sizeof(float)) return stack_launch_meanclip_smem(frames, a, st);
+            break;
+        case FAM_SORT_MED: return stack_dispatch_sorted<MODE_MED, T>(N, frames, a, st);
+        case FAM_SORT_MEDUNC: return stack_dispatch_sorted<MODE_MEDUNC, T>(N, frames, a, st);
+        case FAM_SORT_MEDMAD1: return stack_dispatch_sorted<MODE_MEDMAD1, T>(N, frames, a, st);
         default: break;
     }
     return stack_launch_generic(frames, a, st);
+}
+
+}  // namespace apgpu_stack
+
+extern "C" int apgpu_stack_reduce_f32(const float* const* frames, int N, int64_t H, int64_t W,
+                                      int64_t row0, int64_t nrows, int method,
+                                      double k_lo, double k_hi, int maxiters, int cen, int dev,
+                                      void* out_data, int out_is_f64,
+                                      void* out_nrej, int nrej_is_u16,
+                                      void* out_uncert, uint8_t* out_allmasked,
+                                      int flags, apgpu_stream_t stream) {
+    return stack_reduce_impl<float>(frames, APGPU_U16_NATIVE, N, H, W, row0, nrows, method, k_lo, k_hi, maxiters, cen, dev,
+                                    out_data, out_is_f64, out_nrej, nrej_is_u16, out_uncert, out_allmasked, flags, stream);
+}
+
+extern "C" int apgpu_stack_reduce_u16(const uint16_t* const* frames, int u16_format, int N, int64_t H, int64_t W,
+                                      int64_t row0, int64_t nrows, int method,
+                                      double k_lo, double k_hi, int maxiters, int cen, int dev,
+                                      void* out_data, int out_is_f64,
+                                      void* out_nrej, int nrej_is_u16,
+                                      void* out_uncert, uint8_t* out_allmasked,
+                                      int flags, apgpu_stream_t stream) {
+    return stack_reduce_impl<uint16_t>(frames, u16_format, N, H, W, row0, nrows, method, k_lo, k_hi, maxiters, cen, dev,
+                                       out_data, out_is_f64, out_nrej, nrej_is_u16, out_uncert, out_allmasked, flags, stream);
 }

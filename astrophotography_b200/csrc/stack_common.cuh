@@ -61,20 +61,52 @@ struct StackArgs {
     int tiles_per_warp;          // tensor-map staged kernels: warp tiles per warp (per group) per CTA
     int box_rows, nchunks;       // warp-cooperative kernel: rows per TMA box, boxes per tile
     int one, minus_one;          // +1 / -1 as run-time values (sorted kernels: IMAD on the FMA pipe)
+    // uint16 frames (apgpu_stack_reduce_u16): a raw 16-bit sample r becomes the float
+    //     int_as_float(prmt(r, 0x4B000000, u16_sel) ^ u16_xor) = 2^23 + value      (U16_BIAS + value, exact)
+    // u16_sel picks the byte order (0x7610 host order, 0x7601 FITS big-endian), u16_xor = 0x8000 folds the
+    // BZERO = 32768 offset of FITS unsigned frames (stored value s = v - 32768 as int16: v = s ^ 0x8000).
+    uint32_t u16_sel, u16_xor;
+    float sample_bias;           // what the staged samples carry on top of their value: U16_BIAS or 0
 };
 
-template <int CAP> struct FramePtrs {
-    const float* p[CAP];
-    __device__ __forceinline__ const float* frame(int i) const { return p[i]; }
+constexpr float U16_BIAS = 8388608.f;               // 2^23
+
+// decode one raw 16-bit sample (zero-extended in r) to U16_BIAS + value: two ALU-pipe instructions
+__device__ __forceinline__ float u16_biased(uint32_t r, const StackArgs& a) {
+    return __uint_as_float(__byte_perm(r, 0x4B000000u, a.u16_sel) ^ a.u16_xor);
+}
+// one sample of a frame as its float32 value (direct global load)
+__device__ __forceinline__ float load_sample(const float* p, const StackArgs&) { return ld_stream(p); }
+__device__ __forceinline__ float load_sample(const uint16_t* p, const StackArgs& a) {
+    return u16_biased((uint32_t)__ldcs(p), a) - U16_BIAS;
+}
+// the same, still carrying sample_bias (kernels that shift by a pivot anyway)
+__device__ __forceinline__ float load_sample_biased(const float* p, const StackArgs&) { return ld_stream(p); }
+__device__ __forceinline__ float load_sample_biased(const uint16_t* p, const StackArgs& a) {
+    return u16_biased((uint32_t)__ldcs(p), a);
+}
+// a staged (shared-memory) sample, biased
+__device__ __forceinline__ float staged_sample_biased(const float* s, const StackArgs&) { return *s; }
+__device__ __forceinline__ float staged_sample_biased(const uint16_t* s, const StackArgs& a) {
+    return u16_biased((uint32_t)*s, a);
+}
+template <typename T> __host__ __device__ constexpr float sample_bias_of() { return sizeof(T) == 2 ? U16_BIAS : 0.f; }
+
+template <int CAP, typename T = float> struct FramePtrs {
+    typedef T sample_t;
+    const T* p[CAP];
+    __device__ __forceinline__ const T* frame(int i) const { return p[i]; }
 };
 // equally spaced frames (a [N][H*W] cube): frame i starts stride bytes after frame i-1
-struct CubeFrames {
+template <typename T = float> struct CubeFramesT {
+    typedef T sample_t;
     const char* base;
     int64_t stride;
-    __device__ __forceinline__ const float* frame(int i) const {
-        return reinterpret_cast<const float*>(base + (int64_t)i * stride);
+    __device__ __forceinline__ const T* frame(int i) const {
+        return reinterpret_cast<const T*>(base + (int64_t)i * stride);
     }
 };
+typedef CubeFramesT<float> CubeFrames;
 
 __device__ __forceinline__ bool finite_f(float x) { return fabsf(x) <= FLT_MAX; }
 
@@ -140,7 +172,7 @@ __device__ __forceinline__ double mad_sorted(const float* s, int sa, int sb, dou
     return (m & 1) ? d1 : __dmul_rn(__dadd_rn(d1, d2), 0.5);
 }
 
-template <int CAP, typename Frames = FramePtrs<CAP>>
+template <int CAP, typename Frames = FramePtrs<CAP, float>>
 __device__ __noinline__ void generic_pixel(const Frames& fp, const StackArgs& a, int64_t p) {
     float v[CAP];      // frame order; NaN marks a sample that is not (or no longer) used
     float s[CAP];      // the used samples, ascending
@@ -150,7 +182,7 @@ __device__ __noinline__ void generic_pixel(const Frames& fp, const StackArgs& a,
                              (clip && (a.cen == APGPU_CEN_MEDIAN || a.dev == APGPU_DEV_MAD_STD));
     int nk = 0;
     for (int i = 0; i < N; ++i) {
-        float x = ld_stream(fp.frame(i) + p);
+        float x = load_sample(fp.frame(i) + p, a);
         // sigma_clip rejects non-finite samples up front; without clipping the
         // nan-functions only skip NaN.
         bool ok = clip ? finite_f(x) : (x == x);
@@ -287,11 +319,19 @@ __device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* t
 struct Bucket { int nb, nlo; };
 
 // Equally spaced frames (a [N][H*W] cube) can be described by one 2-D TMA tensor map.
-bool stack_is_cube(const float* const* frames, int N, int64_t npix_end);
+bool stack_is_cube_bytes(const void* const* frames, int N, int64_t npix_end, int elem_bytes);
+template <typename T> inline bool stack_is_cube(const T* const* frames, int N, int64_t npix_end) {
+    return stack_is_cube_bytes(reinterpret_cast<const void* const*>(frames), N, npix_end, (int)sizeof(T));
+}
 // dim0 = pixel (npix_end of them, contiguous), dim1 = frame (N, stride_bytes apart); box = box_pix x box_rows
-// (box_rows = 0: all N frames in one box, N <= 256).
-bool encode_stack_tensor_map(CUtensorMap* tmap, const float* base, uint64_t npix_end, int N,
-                             uint64_t stride_bytes, int box_pix, int box_rows = 0, bool swizzle128 = false);
+// (box_rows = 0: all N frames in one box, N <= 256).  elem_bytes 4 = float32, 2 = uint16.
+bool encode_stack_tensor_map_bytes(CUtensorMap* tmap, const void* base, int elem_bytes, uint64_t npix_end, int N,
+                                   uint64_t stride_bytes, int box_pix, int box_rows, bool swizzle128);
+template <typename T>
+inline bool encode_stack_tensor_map(CUtensorMap* tmap, const T* base, uint64_t npix_end, int N,
+                                    uint64_t stride_bytes, int box_pix, int box_rows = 0, bool swizzle128 = false) {
+    return encode_stack_tensor_map_bytes(tmap, base, (int)sizeof(T), npix_end, N, stride_bytes, box_pix, box_rows, swizzle128);
+}
 
 // what the last apgpu_stack_reduce_f32 call of this thread launched (tests / bench bookkeeping)
 void stack_note_staging(int staging);
@@ -301,10 +341,13 @@ int stack_median_tiles_per_cta();
 
 // cross-translation-unit launchers (one .cu per kernel family so that nvcc compiles them in parallel)
 int stack_launch_generic(const float* const* frames, const StackArgs& a, cudaStream_t st);
-int stack_dispatch_meanclip(int nb, const float* const* frames, const StackArgs& a, cudaStream_t st, int flags);
+int stack_launch_generic(const uint16_t* const* frames, const StackArgs& a, cudaStream_t st);
 int stack_dispatch_meanclip_lo(int nb, const float* const* frames, const StackArgs& a, cudaStream_t st, int flags);
 int stack_dispatch_meanclip_mid(int nb, const float* const* frames, const StackArgs& a, cudaStream_t st, int flags);
 int stack_dispatch_meanclip_hi(int nb, const float* const* frames, const StackArgs& a, cudaStream_t st, int flags);
+int stack_dispatch_meanclip_lo(int nb, const uint16_t* const* frames, const StackArgs& a, cudaStream_t st, int flags);
+int stack_dispatch_meanclip_mid(int nb, const uint16_t* const* frames, const StackArgs& a, cudaStream_t st, int flags);
+int stack_dispatch_meanclip_hi(int nb, const uint16_t* const* frames, const StackArgs& a, cudaStream_t st, int flags);
 int stack_launch_meanclip_smem(const float* const* frames, const StackArgs& a, cudaStream_t st);
 // long stacks (N > 100) on equally spaced frames -- warp-cooperative kernels up to N = 512, lane-split
 // cp.async kernels beyond: returns APGPU_ERR_UNSUPPORTED when there
@@ -315,7 +358,19 @@ int stack_dispatch_meanclip_split_p8(const float* const* frames, const StackArgs
 int stack_dispatch_meanclip_coop_p2(const float* const* frames, const StackArgs& a, cudaStream_t st, int64_t* done_pix);
 int stack_dispatch_meanclip_coop_p4(const float* const* frames, const StackArgs& a, cudaStream_t st, int64_t* done_pix);
 int stack_dispatch_meanclip_coop_p8(const float* const* frames, const StackArgs& a, cudaStream_t st, int64_t* done_pix);
-int stack_dispatch_sorted_med(int nb, const float* const* frames, const StackArgs& a, cudaStream_t st);
-int stack_dispatch_sorted_medmad1(int nb, const float* const* frames, const StackArgs& a, cudaStream_t st);
+// sorted<NB, NLO, MODE> kernels (stack_sorted.cuh).  One translation unit per (mode, sample type, bucket part):
+// the unrolled networks are slow to compile (10-25 s per bucket), so the explicit instantiations
+// dispatch_sorted_part<MODE, T, PART> are spread over many files that nvcc compiles in parallel.
+constexpr int MODE_MED = 0;       // method=median, no clipping
+constexpr int MODE_MEDMAD1 = 1;   // one median/MAD clip pass, then the mean (ApMasterCal)
+constexpr int MODE_MEDUNC = 2;    // method=median, no clipping, uncertainty = 1.4826 * MAD / sqrt(N)
+constexpr int SORT_PARTS = 4;
+__host__ __device__ constexpr int sorted_part_of(int nb) { return nb <= 40 ? 0 : (nb <= 80 ? 1 : (nb <= 112 ? 2 : 3)); }
+// float32 median and median/MAD clip use the fine bucket list; the uncertainty mode and every uint16 mode the
+// coarse one (fewer instantiations; a coarser bucket only costs a little padding work)
+template <int MODE, typename T> constexpr bool sorted_fine_buckets() { return sizeof(T) == 4 && MODE != MODE_MEDUNC; }
+template <int MODE, typename T, int PART>
+int dispatch_sorted_part(int nb, const T* const* frames, const StackArgs& a, cudaStream_t st);
+
 
 }  // namespace apgpu_stack

@@ -440,7 +440,8 @@ __device__ __forceinline__ void meanclip_pixel(float2 (&y)[NB / 2], const Frames
         if (uncertain || nk == 0) { generic_pixel<CAPG, Frames>(fp, a, p); return; }
     }
     const double cy = __ddiv_rn(sum1, (double)nk);
-    const double mean = __dadd_rn((double)pivot, cy);
+    // (uint16 frames are staged as 2^23 + value: pivot - sample_bias is the pivot's value, exactly)
+    const double mean = __dadd_rn((double)(pivot - a.sample_bias), cy);
     double unc_out = (double)NAN;
     if (a.uncert) {
         double var = __dsub_rn(__ddiv_rn(sum2, (double)nk), __dmul_rn(cy, cy));
@@ -451,19 +452,19 @@ __device__ __forceinline__ void meanclip_pixel(float2 (&y)[NB / 2], const Frames
 
 // Direct kernel: one block per 128-pixel tile, samples loaded straight from
 // global memory.
-template <int NB, int NLO, bool SYM>
+template <int NB, int NLO, bool SYM, typename T>
 __global__ void __launch_bounds__(TPB, meanclip_min_blocks(NB))
-stack_meanclip_kernel(const __grid_constant__ FramePtrs<NB> fp, const __grid_constant__ StackArgs a) {
+stack_meanclip_kernel(const __grid_constant__ FramePtrs<NB, T> fp, const __grid_constant__ StackArgs a) {
     const int64_t p = a.pix0 + (int64_t)blockIdx.x * TPB + threadIdx.x;
     if (p >= a.pix0 + a.npix) return;
     const uint32_t p32 = (uint32_t)p;                  // host guarantees H*W < 2^32
     float2 y[NB / 2];
 #pragma unroll
     for (int j = 0; j < NB / 2; ++j) {                 // padding slots point at frame 0 (masked later)
-        y[j].x = ld_stream(fp.p[2 * j] + p32);
-        y[j].y = ld_stream(fp.p[2 * j + 1] + p32);
+        y[j].x = load_sample_biased(fp.p[2 * j] + p32, a);
+        y[j].y = load_sample_biased(fp.p[2 * j + 1] + p32, a);
     }
-    meanclip_pixel<NB, NLO, SYM>(y, fp, a, p);
+    meanclip_pixel<NB, NLO, SYM, NoHook, 1, FramePtrs<NB, T>>(y, fp, a, p);
 }
 
 // ---------------------------------------------------------------------------
@@ -591,6 +592,68 @@ stack_meanclip_tmap_kernel(const __grid_constant__ CUtensorMap tmap, const __gri
     }
 }
 
+// The same pipeline for uint16 frames (apgpu_stack_reduce_u16).  A 128-byte row of the stage now holds 64
+// pixels (narrower rows lose bandwidth in proportion: a fixed number of requests in flight per SM), so a
+// warp tile is 64 pixels x N frames and the warp reduces it in two halves of 32 pixels -- the same
+// shared-memory footprint and the same bytes per copy as the float32 kernel, twice the pixels.  A raw
+// sample becomes the float 2^23 + value with two ALU-pipe instructions (PRMT picks the byte order and puts
+// the exponent byte on top, LOP3 folds FITS' BZERO): the pivot shift y = x - pivot that the algorithm does
+// anyway then removes the 2^23 again, exactly, so the integer-to-float conversion costs no conversion
+// instruction (I2F runs at a quarter of the rate).
+constexpr int WT16 = 64;
+
+template <int NB, int NLO, bool SYM>
+__global__ void __launch_bounds__(TPB, meanclip_min_blocks(NB))
+stack_meanclip_tmap16_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FramePtrs<NB, uint16_t> fp,
+                             const __grid_constant__ StackArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint16_t* stage = reinterpret_cast<uint16_t*>(smem_raw) + (size_t)warp * NB * WT16;   // [NB][64]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)(TPB / 32) * NB * WT16 * sizeof(uint16_t)) + warp;
+    const int N = a.N;
+    if (lane == 0) mbar_init(bar, 1);
+    for (int i = N * WT16 + lane; i < NB * WT16; i += 32) stage[i] = 0;       // padding rows: never copied into
+    __syncwarp();
+    const int pix0 = (int)a.pix0;
+    auto issue = [&](int t) {
+        mbar_expect_tx(bar, (uint32_t)a.N * WT16 * sizeof(uint16_t));
+        tma_load_2d(stage, &tmap, pix0 + t * WT16, 0, bar, l2_evict_first_policy());
+    };
+    const int ntiles = (int)(a.npix / WT16);                                  // full warp tiles (host launches the tail)
+    const int run = (TPB / 32) * a.tiles_per_warp;
+    int tile = (int)blockIdx.x * run + warp;
+    const int tile_end = min((int)(blockIdx.x + 1) * run, ntiles);
+    constexpr int nwarps = TPB / 32;
+    uint32_t parity = 0;
+    if (tile < tile_end && lane == 0) issue(tile);
+    for (; tile < tile_end; tile += nwarps) {
+        while (!mbar_try_wait(bar, parity)) {}
+        parity ^= 1u;
+        const int next = tile + nwarps;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            const uint16_t* col = stage + half * 32 + lane;
+            float2 y[NB / 2];
+#pragma unroll
+            for (int j = 0; j < NB / 2; ++j) {
+                y[j].x = staged_sample_biased(col + (2 * j) * WT16, a);
+                y[j].y = staged_sample_biased(col + (2 * j + 1) * WT16, a);
+            }
+            // the stage is re-armed once the second half's samples have been consumed
+            auto rearm = [&](float s2) {
+                __syncwarp();
+                if (half == 1 && lane == 0 && next < tile_end && s2 != -1.f) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    issue(next);
+                }
+                __syncwarp();
+            };
+            meanclip_pixel<NB, NLO, SYM, decltype(rearm), 1, FramePtrs<NB, uint16_t>>(
+                y, fp, a, (int64_t)(uint32_t)(pix0 + tile * WT16 + half * 32 + lane), rearm);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // cp.async-staged persistent kernel: warp-granular software pipeline
 // ---------------------------------------------------------------------------
@@ -658,11 +721,34 @@ stack_meanclip_cpasync_kernel(const __grid_constant__ FramePtrs<NB> fp, const __
     }
 }
 
-template <int NB, int NLO, bool SYM>
-int launch_meanclip_sym(const FramePtrs<NB>& fp, const StackArgs& a, int staging, cudaStream_t st) {
+template <int NB, int NLO, bool SYM, typename T>
+int launch_meanclip_sym(const FramePtrs<NB, T>& fp, const StackArgs& a, int staging, cudaStream_t st) {
     // staging: 0 direct global loads, 1 CTA-wide TMA bulk copies, 2 warp-granular cp.async pipeline,
     //          3 warp-granular tensor-map TMA pipeline (equally spaced frames only)
+    // (uint16 frames: 3 or 0 only)
     StackArgs rest = a;
+    if constexpr (sizeof(T) == 2) {
+        if (staging == 3) {
+            const int64_t ntiles = a.npix / WT16;
+            CUtensorMap tmap;
+            const int64_t stride = (const char*)fp.p[1] - (const char*)fp.p[0];
+            if (ntiles > 0 && encode_stack_tensor_map(&tmap, fp.p[0], (uint64_t)(a.pix0 + a.npix), a.N, (uint64_t)stride, WT16)) {
+                const size_t smem = (size_t)(TPB / 32) * NB * WT16 * sizeof(uint16_t) + (TPB / 32) * sizeof(uint64_t);
+                APGPU_CUDA(cudaFuncSetAttribute(stack_meanclip_tmap16_kernel<NB, NLO, SYM>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                StackArgs at = a;
+                at.tiles_per_warp = stack_tmap_tiles_per_warp();
+                const int64_t run = (int64_t)(TPB / 32) * at.tiles_per_warp;
+                const int64_t grid = (ntiles + run - 1) / run;
+                stack_meanclip_tmap16_kernel<NB, NLO, SYM><<<(unsigned)grid, TPB, smem, st>>>(tmap, fp, at);
+                APGPU_LAUNCH_CHECK("stack_meanclip_tmap16_kernel");
+                rest.pix0 = a.pix0 + ntiles * WT16;          // the < 64-pixel tail goes through the direct kernel
+                rest.npix = a.npix - ntiles * WT16;
+            } else {
+                stack_note_staging(0);
+            }
+        }
+    } else {
     if (staging == 3) {
         const int64_t ntiles = a.npix / WT;
         CUtensorMap tmap;
@@ -715,18 +801,19 @@ int launch_meanclip_sym(const FramePtrs<NB>& fp, const StackArgs& a, int staging
             rest.npix = a.npix - ntiles * TTPB;
         }
     }
+    }
     if (rest.npix > 0) {
         int64_t blocks = (rest.npix + TPB - 1) / TPB;
-        stack_meanclip_kernel<NB, NLO, SYM><<<(unsigned)blocks, TPB, 0, st>>>(fp, rest);
+        stack_meanclip_kernel<NB, NLO, SYM, T><<<(unsigned)blocks, TPB, 0, st>>>(fp, rest);
         APGPU_LAUNCH_CHECK("stack_meanclip_kernel");
     }
     return APGPU_OK;
 }
 
-template <int NB, int NLO>
-int launch_meanclip(const float* const* frames, const StackArgs& a_in, cudaStream_t st, int flags) {
+template <int NB, int NLO, typename T>
+int launch_meanclip(const T* const* frames, const StackArgs& a_in, cudaStream_t st, int flags) {
     static_assert(NB - NLO <= MEANCLIP_MAX_TAIL, "tail mask too small");
-    FramePtrs<NB> fp;
+    FramePtrs<NB, T> fp;
     for (int i = 0; i < NB; ++i) fp.p[i] = i < a_in.N ? frames[i] : frames[0];   // padding: loaded, then masked
     StackArgs a = a_in;
     for (int i = NLO; i < NB; ++i) a.tailmask[i - NLO] = i < a.N ? 1.f : 0.f;
@@ -738,9 +825,10 @@ int launch_meanclip(const float* const* frames, const StackArgs& a_in, cudaStrea
     if (flags & APGPU_STACK_DIRECT_LOADS) staging = 0;
     if (flags & APGPU_STACK_USE_CPASYNC) staging = 2;
     if (flags & APGPU_STACK_USE_TENSORMAP) staging = 3;
+    if (sizeof(T) == 2 && staging != 3) staging = 0;     // uint16 frames: tensor-map TMA or direct loads
     // (a TMA box must start on a 16-byte boundary: found by tests/test_gpu_stack.py::test_meanclip_row_band_on_cube)
-    if (staging == 3 && (!stack_is_cube(frames, a.N, a.pix0 + a.npix) || a.pix0 % 4 != 0))
-        staging = (flags & APGPU_STACK_USE_TENSORMAP) ? 0 : ((NB > 32 && NB <= 80) ? 2 : 0);   // measured (time_variant.py)
+    if (staging == 3 && (!stack_is_cube(frames, a.N, a.pix0 + a.npix) || (a.pix0 * (int64_t)sizeof(T)) % 16 != 0))
+        staging = (sizeof(T) == 2 || (flags & APGPU_STACK_USE_TENSORMAP)) ? 0 : ((NB > 32 && NB <= 80) ? 2 : 0);   // measured (time_variant.py)
     // the per-warp stages must leave room for meanclip_min_blocks CTAs per SM
     const size_t smem_cta = (size_t)NB * sizeof(float*) + (size_t)(TPB / 32) * NB * WT * sizeof(float);
     if ((staging == 2 || staging == 3) && smem_cta * meanclip_min_blocks(NB) > (size_t)SMEM_MAX_BYTES) staging = 0;
@@ -749,10 +837,10 @@ int launch_meanclip(const float* const* frames, const StackArgs& a_in, cudaStrea
         for (int i = 0; i < a.N; ++i)
             if (!apgpu_aligned(frames[i] + a.pix0, 16)) staging = 0;
     stack_note_staging(staging);
-    if ((float)a.klo == (float)a.khi) return launch_meanclip_sym<NB, NLO, true>(fp, a, staging, st);
-    return launch_meanclip_sym<NB, NLO, false>(fp, a, staging, st);
+    if ((float)a.klo == (float)a.khi) return launch_meanclip_sym<NB, NLO, true, T>(fp, a, staging, st);
+    return launch_meanclip_sym<NB, NLO, false, T>(fp, a, staging, st);
 }
 
-#define MC_CASE(NB_, NLO_) if (nb == NB_) return launch_meanclip<NB_, NLO_>(frames, a, st, flags);
+#define MC_CASE(NB_, NLO_) if (nb == NB_) return launch_meanclip<NB_, NLO_, MC_T>(frames, a, st, flags);
 
 }  // namespace apgpu_stack

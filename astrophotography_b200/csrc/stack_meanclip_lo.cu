@@ -1,5 +1,6 @@
-// meanclip<NB, NLO> instantiations, part "lo" (split so that nvcc compiles the buckets in parallel)
+// meanclip<NB, NLO> instantiations, part "lo", float frames (split so that nvcc compiles the buckets in parallel)
 #include "stack_meanclip.cuh"
+#define MC_T float
 
 namespace apgpu_stack {
 

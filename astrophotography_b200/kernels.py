@@ -15,6 +15,7 @@ METHODS = {"median": 0, "average": 1, "mean": 1, "min": 2, "max": 3}
 CENFUNCS = {"mean": 0, "median": 1}
 DEVFUNCS = {"std": 0, "mad_std": 1}
 _FORCE_GENERIC = 1
+U16_FORMATS = {"native": 0, "fits": 1}        # include/apgpu.h: APGPU_U16_NATIVE / APGPU_U16_FITS_BZERO
 _PREFER = {None: 0, "registers": 2, "shared": 4, "registers_tma": 2 | 8, "tma": 8,
            "registers_direct": 2 | 16, "direct": 16, "registers_cpasync": 2 | 32, "cpasync": 32,
            "registers_tensormap": 2 | 64, "tensormap": 64}
@@ -58,36 +59,46 @@ def _maxiters(maxiters):
 
 def stack_reduce(frames, method="average", k_lo=5.0, k_hi=5.0, maxiters=1, cen="median",
                  dev="mad_std", row0=0, nrows=None, out_f64=False, want_nrej=True,
-                 want_uncert=False, want_allmasked=False, force_generic=False, out=None, prefer=None):
-    """Per-pixel combine of N frames (``apgpu_stack_reduce_f32``).
+                 want_uncert=False, want_allmasked=False, force_generic=False, out=None, prefer=None,
+                 u16_format="native"):
+    """Per-pixel combine of N frames (``apgpu_stack_reduce_f32`` / ``apgpu_stack_reduce_u16``).
 
-    ``frames``: a (N,H,W) float32 CUDA tensor or a sequence of N (H,W) float32
-    CUDA tensors.  Defaults are the reference's ApMasterCal settings
-    (scripts/ap_combine_darks.py:394-399): average after one 5-sigma
-    median/MAD clip.  Returns a dict of (H,W) tensors: ``data``, and when
-    requested ``nrej`` (uint8, or uint16 for N>255), ``uncert``, ``allmasked``.
-    Only rows ``[row0, row0+nrows)`` are written.
+    ``frames``: a (N,H,W) CUDA tensor or a sequence of N (H,W) CUDA tensors, float32 or
+    uint16 (int16 tensors are taken as the raw 16-bit samples).  uint16 frames are
+    converted inside the load phase of the kernels; ``u16_format="fits"`` means the
+    samples are the data unit of a BITPIX=16 / BZERO=32768 FITS file as stored on disk
+    (big-endian int16 + 32768).  Defaults are the reference's ApMasterCal settings
+    (scripts/ap_combine_darks.py:394-399): average after one 5-sigma median/MAD clip.
+    Returns a dict of (H,W) tensors: ``data``, and when requested ``nrej`` (uint8, or
+    uint16 for N>255), ``uncert``, ``allmasked``.  Only rows ``[row0, row0+nrows)`` are
+    written.
     """
     torch = _native.require_cuda()
     lib = _native.load()
+    sample_dtypes = (torch.float32, torch.uint16, torch.int16)
     if isinstance(frames, torch.Tensor):
         if frames.dim() != 3:
             raise RuntimeError("stack_reduce: frame cube must be (N, H, W)")
-        _check_image(torch, frames, "frames", torch.float32)
+        _check_image(torch, frames, "frames")
         flist = [frames[i] for i in range(frames.shape[0])]
     else:
         flist = list(frames)
         for i, f in enumerate(flist):
-            _check_image(torch, f, f"frames[{i}]", torch.float32)
+            _check_image(torch, f, f"frames[{i}]")
     n = len(flist)
     if n == 0:
         raise RuntimeError("stack_reduce: no frames")
+    dt = flist[0].dtype
+    if dt not in sample_dtypes or any(f.dtype != dt for f in flist):
+        raise RuntimeError(f"stack_reduce: frames must all be float32 or all be uint16, got {dt}")
     h, w = flist[0].shape
     for f in flist:
         if tuple(f.shape) != (h, w):
             raise RuntimeError("stack_reduce: frames differ in shape")
     if method not in METHODS or cen not in CENFUNCS or dev not in DEVFUNCS:
         raise RuntimeError(f"stack_reduce: bad method/cen/dev {method}/{cen}/{dev}")
+    if u16_format not in U16_FORMATS:
+        raise RuntimeError(f"stack_reduce: bad u16_format {u16_format}")
     if nrows is None:
         nrows = h - row0
     device = flist[0].device
@@ -102,15 +113,20 @@ def stack_reduce(frames, method="average", k_lo=5.0, k_hi=5.0, maxiters=1, cen="
         res["allmasked"] = torch.empty((h, w), dtype=torch.uint8, device=device)
     ptrs = (ctypes.c_void_p * n)(*[f.data_ptr() for f in flist])
     nrej = res.get("nrej") if want_nrej else None
-    st = lib.apgpu_stack_reduce_f32(
-        ptrs, n, h, w, int(row0), int(nrows), METHODS[method], float(k_lo), float(k_hi),
-        _maxiters(maxiters), CENFUNCS[cen], DEVFUNCS[dev],
-        _ptr(res["data"]), int(res["data"].dtype == torch.float64),
-        _ptr(nrej), int(nrej is not None and nrej.dtype == torch.uint16),
-        _ptr(res.get("uncert") if want_uncert else None),
-        _ptr(res.get("allmasked") if want_allmasked else None),
-        (_FORCE_GENERIC if force_generic else 0) | _PREFER[prefer], _stream(torch))
-    _native.check(st, "apgpu_stack_reduce_f32")
+    flags = (_FORCE_GENERIC if force_generic else 0) | _PREFER[prefer]
+    tail = (int(row0), int(nrows), METHODS[method], float(k_lo), float(k_hi),
+            _maxiters(maxiters), CENFUNCS[cen], DEVFUNCS[dev],
+            _ptr(res["data"]), int(res["data"].dtype == torch.float64),
+            _ptr(nrej), int(nrej is not None and nrej.dtype == torch.uint16),
+            _ptr(res.get("uncert") if want_uncert else None),
+            _ptr(res.get("allmasked") if want_allmasked else None),
+            flags, _stream(torch))
+    if dt == torch.float32:
+        st = lib.apgpu_stack_reduce_f32(ptrs, n, h, w, *tail)
+        _native.check(st, "apgpu_stack_reduce_f32")
+    else:
+        st = lib.apgpu_stack_reduce_u16(ptrs, U16_FORMATS[u16_format], n, h, w, *tail)
+        _native.check(st, "apgpu_stack_reduce_u16")
     return res
 
 

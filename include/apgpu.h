@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define APGPU_ABI_VERSION 1
+#define APGPU_ABI_VERSION 2
 
 #define APGPU_OK 0
 #define APGPU_ERR_ARG 1         /* bad argument (null pointer, bad size, bad enum) */
@@ -83,6 +83,27 @@ enum { APGPU_DEV_STD = 0, APGPU_DEV_MAD_STD = 1 };
 #define APGPU_STACK_MAX_FRAMES 1024
 
 int apgpu_stack_reduce_f32(const float* const* frames, int N, int64_t H, int64_t W,
+                           int64_t row0, int64_t nrows, int method,
+                           double k_lo, double k_hi, int maxiters, int cen, int dev,
+                           void* out_data, int out_is_f64,
+                           void* out_nrej, int nrej_is_u16,
+                           void* out_uncert, uint8_t* out_allmasked,
+                           int flags, apgpu_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * The same reducer on raw 16-bit frames: the integer -> float32 conversion of
+ * _read_fits (core/ApCalibrate.py:303-307; raw frames are BITPIX 16 / BZERO 32768,
+ * doc/fits_metadata.md:70-76) is fused into the load phase, so a frame costs
+ * 2 bytes per pixel over PCIe and HBM.  Results are those of apgpu_stack_reduce_f32
+ * on float32(frames).
+ *
+ * u16_format  APGPU_U16_NATIVE      host-order uint16 samples (what astropy hands out with uint=True)
+ *             APGPU_U16_FITS_BZERO  the data unit of a BITPIX=16, BZERO=32768 FITS image as it is on
+ *                                   disk: big-endian int16 s, value = s + 32768
+ * PEDESTAL is not applied here: like ccdproc.combine the master keeps the keyword.
+ * ---------------------------------------------------------------------- */
+enum { APGPU_U16_NATIVE = 0, APGPU_U16_FITS_BZERO = 1 };
+int apgpu_stack_reduce_u16(const uint16_t* const* frames, int u16_format, int N, int64_t H, int64_t W,
                            int64_t row0, int64_t nrows, int method,
                            double k_lo, double k_hi, int maxiters, int cen, int dev,
                            void* out_data, int out_is_f64,

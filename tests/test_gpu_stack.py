@@ -418,3 +418,142 @@ def test_real_ccdproc_cross_check_on_this_box(cuda):
     assert np.allclose(np.asarray(ref.data), mine["data"], rtol=1e-12)
     got = _run(torch, st, out_f64=True)
     assert np.allclose(got["data"], np.asarray(ref.data), rtol=1e-12)
+
+
+# ---------------------------------------------------------------- median/MAD clip extremes, median + uncertainty
+@pytest.mark.parametrize("n", [21, 30, 64, 100, 128, 200])
+def test_medmad_uncert_and_frame_order_mean(cuda, n):
+    """The reference's ApMasterCal setting with the uncertainty plane (what ApMasterCal always asks for):
+    rejection maps identical, unclipped pixels' float64 mean bit-identical to np.nanmean (frame-order sum)."""
+    torch = cuda
+    st = _stack(n, (13, 84), seed=120 + n, quantise=(n % 2 == 0))
+    for k_lo, k_hi in ((5.0, 5.0), (2.0, 3.0)):
+        e = _oracle(st, "average", k_lo, k_hi, 1, "median", "mad_std")
+        for out_f64 in (False, True):
+            got = _run(torch, st, method="average", k_lo=k_lo, k_hi=k_hi, maxiters=1, cen="median", dev="mad_std",
+                       out_f64=out_f64, want_uncert=True)
+            assert np.array_equal(got["nrej"].astype(np.int64), e["nrej"])
+            assert np.array_equal(got["allmasked"], e["allmasked"])
+            _assert_close_data(got["data"].astype(np.float64), e["data"], RTOL32 if not out_f64 else 1e-13, 12.0)
+            _assert_close_data(got["uncert"].astype(np.float64), e["uncert"], 1e-5 if not out_f64 else 1e-12, 1e-3)
+            if out_f64:
+                keep_all = (e["nrej"] == 0) & np.isfinite(e["data"])
+                assert np.array_equal(got["data"][keep_all], e["data"][keep_all])
+
+
+def test_medmad_constant_frames_and_outlier_in_every_pixel(cuda):
+    """MAD = 0 (every sample equals the median: nothing clipped) and a stack where every pixel holds an outlier."""
+    torch = cuda
+    n, shape = 40, (6, 96)
+    const = np.full((n,) + shape, 123.0, np.float32)
+    got = _run(torch, const, method="average", out_f64=True, want_uncert=True)
+    assert (got["data"] == 123.0).all() and (got["nrej"] == 0).all() and (got["uncert"] == 0).all()
+    rng = np.random.default_rng(3)
+    st = rng.normal(500, 5, (n,) + shape).astype(np.float32)
+    st[rng.integers(0, n, shape), np.arange(shape[0])[:, None], np.arange(shape[1])[None, :]] += 9000.0
+    exp = _oracle(st, "average", 5.0, 5.0, 1, "median", "mad_std")
+    assert (exp["nrej"] >= 1).all()
+    got = _run(torch, st, method="average", out_f64=True)
+    assert np.array_equal(got["nrej"].astype(np.int64), exp["nrej"])
+    _assert_close_data(got["data"], exp["data"], 1e-13, 1.0)
+
+
+@pytest.mark.parametrize("n", [3, 4, 9, 16, 30, 31, 64, 100, 101, 200])
+def test_median_with_uncertainty_fast_kernel(cuda, n):
+    """ApMasterCal(method='median') always asks for the uncertainty plane: median (bit-exact) +
+    1.4826 * MAD / sqrt(N) from the sorted column, no generic kernel."""
+    torch = cuda
+    from astrophotography_b200 import kernels
+    assert kernels.stack_kernel_name(n, "median", maxiters=0, want_uncert=True).startswith("sorted_median_mad")
+    st = _stack(n, (11, 76), seed=200 + n, quantise=(n % 2 == 1))
+    exp = _oracle(st, "median", 5.0, 5.0, 0, "median", "mad_std")
+    for out_f64 in (False, True):
+        got = _run(torch, st, method="median", maxiters=0, out_f64=out_f64, want_uncert=True)
+        e = exp["data"] if out_f64 else exp["data"].astype(np.float32)
+        assert bits_equal(got["data"], e)
+        assert np.array_equal(got["nrej"].astype(np.int64), exp["nrej"])
+        ok = np.isfinite(exp["uncert"]) & np.isfinite(st).all(axis=0)
+        _assert_close_data(got["uncert"].astype(np.float64)[ok], exp["uncert"][ok], 1e-6 if not out_f64 else 1e-14, 1e-3)
+
+
+# ---------------------------------------------------------------- uint16 frames (f2)
+def _u16_stack(n, shape, seed):
+    from astrophotography_b200 import synth
+    rng = np.random.default_rng(seed)
+    st = synth.dark_stack(n, shape, exptime=300.0, quantise=True)
+    st[:, 0, :4] = np.array([0, 65535, 32767, 32768], np.float32)          # the corners of the format
+    st[rng.integers(0, n), 1, :] += 40000.0
+    return np.clip(st, 0, 65535).astype(np.uint16)
+
+
+def _u16_tensor(torch, u16, fmt):
+    if fmt == "fits":      # the data unit of a BITPIX=16 / BZERO=32768 file: big-endian int16 of (value - 32768)
+        raw = (u16.astype(np.int32) - 32768).astype(">i2")
+        return torch.from_numpy(np.ascontiguousarray(raw).view(np.int16).copy()).cuda()
+    return torch.from_numpy(u16.view(np.int16).copy()).cuda().view(torch.uint16)
+
+
+U16_CASES = [
+    ("average", 5.0, 5.0, 1, "median", "mad_std"),     # ApMasterCal: two-phase sorted kernels
+    ("average", 3.0, 3.0, 5, "mean", "std"),           # kappa-sigma: tensor-map meanclip kernel, 64-pixel tiles
+    ("median", 5.0, 5.0, 0, "median", "mad_std"),      # plain median
+    ("average", 3.0, 3.0, 5, "median", "std"),         # astropy default: generic kernel
+    ("max", 3.0, 3.0, 0, "mean", "std"),
+]
+
+
+@pytest.mark.parametrize("n", [3, 10, 30, 31, 64, 100, 101, 160, 200])
+@pytest.mark.parametrize("case", U16_CASES, ids=lambda c: "-".join(map(str, c)))
+@pytest.mark.parametrize("fmt", ["native", "fits"])
+def test_u16_frames_match_oracle_on_float32_of_them(cuda, n, case, fmt):
+    """apgpu_stack_reduce_u16: raw 16-bit frames (host order, or the big-endian BZERO=32768 data unit of a
+    FITS file) give exactly what the float32 path gives on float32(frames): identical rejection maps,
+    bit-exact selection, means within 1e-6."""
+    torch = cuda
+    from astrophotography_b200 import kernels
+    method, k_lo, k_hi, maxiters, cen, dev = case
+    shape = (9, 200)                                   # 1800 pixels: 64-pixel warp tiles + tails
+    u16 = _u16_stack(n, shape, seed=300 + n)
+    exp = _oracle(u16.astype(np.float32), method, k_lo, k_hi, maxiters, cen, dev)
+    cube = _u16_tensor(torch, u16, fmt)
+    for out_f64 in (False, True):
+        res = kernels.stack_reduce(cube, method=method, k_lo=k_lo, k_hi=k_hi, maxiters=maxiters, cen=cen, dev=dev,
+                                   out_f64=out_f64, want_nrej=True, want_allmasked=True, want_uncert=True, u16_format=fmt)
+        torch.cuda.synchronize()
+        got = {k: v.cpu().numpy() for k, v in res.items()}
+        assert np.array_equal(got["nrej"].astype(np.int64), exp["nrej"]), (case, fmt, out_f64)
+        assert np.array_equal(got["allmasked"], exp["allmasked"])
+        if method in ("median", "max"):
+            e = exp["data"] if out_f64 else exp["data"].astype(np.float32)
+            assert bits_equal(got["data"], e)
+        else:
+            _assert_close_data(got["data"].astype(np.float64), exp["data"], RTOL32 if not out_f64 else 2e-7, 12.0)
+        _assert_close_data(got["uncert"].astype(np.float64), exp["uncert"], 1e-5, 1e-3)
+    # the float32 path on the converted frames gives the same rejection map (same kernels, other loader)
+    f32 = _run(torch, u16.astype(np.float32), method=method, k_lo=k_lo, k_hi=k_hi, maxiters=maxiters, cen=cen, dev=dev)
+    assert np.array_equal(f32["nrej"], got["nrej"])
+
+
+@pytest.mark.parametrize("n,row0,nrows", [(30, 3, 5), (100, 4, 4), (100, 1, 7), (64, 2, 5)])
+def test_u16_row_bands_and_staging(cuda, n, row0, nrows):
+    """Row bands of a uint16 cube: a band starting on a 16-byte boundary keeps the tensor-map path (staging 3),
+    any other start falls back to direct loads; rows outside the band stay untouched."""
+    torch = cuda
+    from astrophotography_b200 import kernels
+    shape = (8, 100)                                   # 200-byte rows: every other row starts on a 16-byte boundary
+    u16 = _u16_stack(n, shape, seed=400 + n)
+    exp = _oracle(u16.astype(np.float32), "average", 3.0, 3.0, 5, "mean", "std")
+    cube = _u16_tensor(torch, u16, "native")
+    out = {"data": torch.full(shape, -7.0, dtype=torch.float32, device="cuda"),
+           "nrej": torch.full(shape, 255, dtype=torch.uint8, device="cuda")}
+    kernels.stack_reduce(cube, method="average", k_lo=3.0, k_hi=3.0, maxiters=5, cen="mean", dev="std",
+                         row0=row0, nrows=nrows, out=out)
+    torch.cuda.synchronize()
+    aligned = (row0 * shape[1] * 2) % 16 == 0
+    assert (kernels.stack_last_staging() == 3) == aligned
+    data, nrej = out["data"].cpu().numpy(), out["nrej"].cpu().numpy()
+    band = slice(row0, row0 + nrows)
+    assert np.array_equal(nrej[band].astype(np.int64), exp["nrej"][band])
+    _assert_close_data(data[band].astype(np.float64), exp["data"][band], RTOL32, 12.0)
+    keep = np.ones(shape[0], bool); keep[band] = False
+    assert (data[keep] == -7.0).all() and (nrej[keep] == 255).all()

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), f"{name} declared in apgpu.h but not exported"
         assert name in _native.SIGNATURES, f"{name} has no ctypes signature in _native.py"
-    assert lib.apgpu_abi_version() == 1
+    assert lib.apgpu_abi_version() == 2
     assert lib.apgpu_last_error() is not None
     assert int(lib.apgpu_flat_norm_workspace_bytes(4096 * 4096)) > 64
     assert int(lib.apgpu_image_stats_workspace_bytes(100)) > 8192
@@ -46,7 +46,8 @@ def test_kernel_selection_is_host_logic():
     assert kernels.stack_kernel_name(200, "average", 3, 3, 5, "mean", "std") == "meanclip_coop<4>"
     assert kernels.stack_kernel_name(1000, "average", 3, 3, 5, "mean", "std") == "meanclip_split<8>"
     assert kernels.stack_kernel_name(30, "median", maxiters=0) == "sorted_median<32>"
-    assert kernels.stack_kernel_name(30, "median", maxiters=0, want_uncert=True).startswith("generic")
+    assert kernels.stack_kernel_name(30, "median", maxiters=0, want_uncert=True) == "sorted_median_mad<32>"
+    assert kernels.stack_kernel_name(300, "median", maxiters=0).startswith("generic")
     assert kernels.stack_kernel_name(30, force_generic=True).startswith("generic")
     assert kernels.stack_kernel_name(600, "average", 3, 3, 5, "mean", "std") == "meanclip_split<8>"
     assert kernels.stack_kernel_name(600, "average", 3, 3, 5, "mean", "std", prefer="registers").startswith("generic")
