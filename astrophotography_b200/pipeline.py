@@ -7,9 +7,16 @@ reference makes when the frames live in host RAM, and what ``bench.py`` times as
 frame is read once, not once per band); band ``k+1`` is uploaded on a copy
 stream while band ``k`` is reduced on the compute stream (two device buffers,
 CUDA events), and each band of the result goes back to pinned host memory as
-soon as it is done.  Multi-GPU: one process per GPU, each owning a contiguous
-row band of every frame (``row_band``); no data-path collective is needed
-because every output pixel depends only on the same pixel of the N frames.
+soon as it is done.  Frames may be float32 or raw uint16 (2 bytes per pixel over
+PCIe and HBM; converted inside the kernels' load phase).
+
+Multi-GPU (``ShardedStackCombiner``): one process per GPU, each owning a contiguous
+row band of every frame (``row_band``).  A rank uploads only its band, reduces it
+and writes its band of the result straight into ONE host array shared by all
+ranks (POSIX shared memory, page-locked in every process): no device round trip,
+no data-path collective -- every output pixel depends only on the same pixel of
+the N frames.  ``torch.distributed`` carries only the name
+of the shared segment and the barriers.
 """
 from __future__ import annotations
 
@@ -32,40 +39,76 @@ def row_band(nrows: int, world: int, rank: int, halo: int = 0):
     return r0, r1, max(0, r0 - halo), min(nrows, r1 + halo)
 
 
+_TORCH_DTYPES = None
+
+
+def _torch_dtype(torch, dtype):
+    global _TORCH_DTYPES
+    if _TORCH_DTYPES is None:
+        _TORCH_DTYPES = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64,
+                         np.dtype(np.uint8): torch.uint8, np.dtype(np.uint16): torch.uint16,
+                         np.dtype(np.int16): torch.int16}
+    return _TORCH_DTYPES[np.dtype(dtype)]
+
+
 def pinned_empty(shape, dtype=np.float32):
-    """A numpy array backed by page-locked host memory (fast, truly async H2D/D2H)."""
+    """A numpy array backed by page-locked host memory (fast, truly async H2D/D2H).
+    Returns ``(array, tensor)``; the tensor owns the memory."""
     torch = _native.require_cuda()
-    tdtype = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64,
-              np.dtype(np.uint8): torch.uint8, np.dtype(np.uint16): torch.uint16,
-              np.dtype(np.int16): torch.int16}[np.dtype(dtype)]
+    tdtype = _torch_dtype(torch, dtype)
     t = torch.empty(tuple(shape), dtype=tdtype, pin_memory=True)
     if tdtype == torch.uint16:
         return t.view(torch.int16).numpy().view(np.uint16), t
     return t.numpy(), t
 
 
+def host_tensor(torch, arr):
+    """A CPU tensor sharing memory with a C-contiguous numpy array (uint16 arrays are
+    wrapped as int16: only the bytes matter to a copy)."""
+    if isinstance(arr, torch.Tensor):
+        return arr
+    if not arr.flags.c_contiguous:
+        raise RuntimeError("host frames must be C-contiguous")
+    if arr.dtype == np.uint16:
+        return torch.from_numpy(arr.view(np.int16))
+    return torch.from_numpy(arr)
+
+
 class HostStackCombiner:
     """Reusable double-buffered host->device->host stack reducer.
 
-    ``combine(frames)`` takes N host frames (a sequence of (H,W) float32 numpy
-    arrays or one (N,H,W) array; pinned memory gives full PCIe speed) and
-    returns host arrays ``data`` (+ ``nrej``, ``uncert``, ``allmasked`` when
-    requested).  Device buffers are allocated once per instance.
+    ``combine(frames)`` takes N host frames -- a sequence of (H,W) numpy arrays or one
+    (N,H,W) array, float32 or uint16 as declared by ``dtype`` (pinned memory gives full
+    PCIe speed) -- and returns host arrays ``data`` (+ ``nrej``, ``uncert``, ``allmasked``
+    when requested).  Device buffers are allocated once per instance.  ``host_out`` may
+    supply the result arrays (e.g. slices of a shared segment that the caller page-locked);
+    by default they are pinned arrays owned by the instance.
     """
 
     def __init__(self, n, h, w, method="average", k_lo=5.0, k_hi=5.0, maxiters=1, cen="median",
                  dev="mad_std", out_f64=False, want_nrej=True, want_uncert=False,
-                 want_allmasked=False, band_bytes=2 << 30, device=None):
+                 want_allmasked=False, band_bytes=2 << 30, device=None, dtype=np.float32,
+                 u16_format="native", host_out=None):
         torch = _native.require_cuda()
         self.torch = torch
         self.n, self.h, self.w = int(n), int(h), int(w)
+        self.dtype = np.dtype(dtype)
+        if self.dtype not in (np.dtype(np.float32), np.dtype(np.uint16)):
+            raise RuntimeError(f"HostStackCombiner: frames must be float32 or uint16, not {self.dtype}")
+        self.u16_format = u16_format
         self.params = dict(method=method, k_lo=k_lo, k_hi=k_hi, maxiters=maxiters, cen=cen, dev=dev)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
-        self.band_rows = int(max(1, min(self.h, band_bytes // (self.n * self.w * 4))))
+        item = self.dtype.itemsize
+        rows = int(max(1, min(self.h, band_bytes // (self.n * self.w * item))))
+        if self.dtype == np.uint16 and rows < self.h:
+            # a uint16 band must start on a 16-byte boundary to keep the tensor-map kernels (8 pixels)
+            step = 8 // int(np.gcd(8, self.w))
+            rows = max(step, rows - rows % step)
+        self.band_rows = rows
         self.nbands = (self.h + self.band_rows - 1) // self.band_rows
         odt = torch.float64 if out_f64 else torch.float32
-        self.cube = [torch.empty((self.n, self.band_rows, self.w), dtype=torch.float32, device=self.device)
-                     for _ in range(2)]
+        cdt = torch.float32 if self.dtype == np.float32 else torch.int16
+        self.cube = [torch.empty((self.n, self.band_rows, self.w), dtype=cdt, device=self.device) for _ in range(2)]
         self.outs = []
         for _ in range(2):
             o = {"data": torch.empty((self.band_rows, self.w), dtype=odt, device=self.device)}
@@ -81,24 +124,35 @@ class HostStackCombiner:
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.compute_stream = torch.cuda.Stream(device=self.device)
         np_odt = np.float64 if out_f64 else np.float32
-        self.host_out = {"data": pinned_empty((self.h, self.w), np_odt)}
+        spec = {"data": np_odt}
         if want_nrej:
-            self.host_out["nrej"] = pinned_empty((self.h, self.w), np.uint8 if self.n <= 255 else np.uint16)
+            spec["nrej"] = np.uint8 if self.n <= 255 else np.uint16
         if want_uncert:
-            self.host_out["uncert"] = pinned_empty((self.h, self.w), np_odt)
+            spec["uncert"] = np_odt
         if want_allmasked:
-            self.host_out["allmasked"] = pinned_empty((self.h, self.w), np.uint8)
-        self.h2d_bytes = self.n * self.h * self.w * 4
+            spec["allmasked"] = np.uint8
+        self.out_spec = spec
+        self._keep = []
+        self.host_out = {}
+        for key, dt in spec.items():
+            if host_out is not None:
+                arr = host_out[key]
+                if arr.shape != (self.h, self.w) or arr.dtype != np.dtype(dt) or not arr.flags.c_contiguous:
+                    raise RuntimeError(f"HostStackCombiner: host_out[{key!r}] must be a C-contiguous {(self.h, self.w)} {np.dtype(dt)} array")
+                self.host_out[key] = (arr, host_tensor(torch, arr))
+            else:
+                arr, t = pinned_empty((self.h, self.w), dt)
+                self.host_out[key] = (arr, t.view(torch.int16) if t.dtype == torch.uint16 else t)
+        self.h2d_bytes = self.n * self.h * self.w * item
         self.d2h_bytes = sum(arr.nbytes for arr, _ in self.host_out.values())
 
     def _frame_tensor(self, frames, i):
-        torch = self.torch
         f = frames[i]
-        if isinstance(f, torch.Tensor):
+        if isinstance(f, self.torch.Tensor):
             return f
-        if f.dtype != np.float32 or not f.flags.c_contiguous:
-            raise RuntimeError("HostStackCombiner: frames must be C-contiguous float32")
-        return torch.from_numpy(f)
+        if f.dtype != self.dtype or not f.flags.c_contiguous:
+            raise RuntimeError(f"HostStackCombiner: frames must be C-contiguous {self.dtype}")
+        return host_tensor(self.torch, f)
 
     def combine(self, frames):
         torch = self.torch
@@ -125,11 +179,11 @@ class HostStackCombiner:
             with torch.cuda.stream(self.compute_stream):
                 self.compute_stream.wait_event(uploaded[buf])
                 kernels.stack_reduce(self.cube[buf], row0=0, nrows=rows, out=self.outs[buf],
-                                     **self.params, **self.want)
+                                     u16_format=self.u16_format, **self.params, **self.want)
                 for key, (_, pinned) in self.host_out.items():
                     src = self.outs[buf][key][:rows]
                     dst = pinned[r0:r1]
-                    if dst.dtype != src.dtype:        # uint16 pinned buffers are int16-backed
+                    if dst.dtype != src.dtype:        # uint16 host arrays are int16-backed
                         src = src.view(dst.dtype)
                     dst.copy_(src, non_blocking=True)
                 ev = torch.cuda.Event()
@@ -139,55 +193,170 @@ class HostStackCombiner:
         return {k: arr for k, (arr, _) in self.host_out.items()}
 
 
-def combine_sharded(frames, reduce_band=None, dist=None, **combine_kw):
+# ---------------------------------------------------------------------------
+# page-locking memory that torch did not allocate (shared segments)
+# ---------------------------------------------------------------------------
+class _HostRegistration:
+    """cudaHostRegister over a numpy array's memory for the life of the object."""
+
+    def __init__(self, torch, arr):
+        self.rt = torch.cuda.cudart()
+        self.ptr = arr.__array_interface__["data"][0]
+        self.nbytes = arr.nbytes
+        self.ok = False
+        if self.nbytes:
+            err = self.rt.cudaHostRegister(self.ptr, self.nbytes, 0)
+            code = int(getattr(err, "value", err))
+            self.ok = code == 0
+            if not self.ok:                         # still correct, only slower (staged copies)
+                self.error = code
+
+    def close(self):
+        if self.ok:
+            self.rt.cudaHostUnregister(self.ptr)
+            self.ok = False
+
+
+class SharedHostArrays:
+    """The same named host arrays mapped by every process of one node (POSIX shared memory).
+
+    Rank 0 creates the segment, the other ranks attach by name (``create_or_attach`` exchanges the
+    name through ``torch.distributed``); ``arrays[key]`` are numpy views.  The creating process unlinks
+    the segment on ``close``."""
+
+    def __init__(self, spec, shape, name=None, create=True):
+        from multiprocessing import shared_memory
+        self.spec = {k: np.dtype(v) for k, v in spec.items()}
+        self.shape = tuple(shape)
+        npix = int(np.prod(self.shape))
+        offs, total = {}, 0
+        for k, dt in self.spec.items():
+            total = (total + 4095) // 4096 * 4096          # page-aligned planes
+            offs[k] = total
+            total += npix * dt.itemsize
+        total = max(total, 1)
+        if create:
+            self.shm = shared_memory.SharedMemory(create=True, size=total)
+        else:
+            self.shm = shared_memory.SharedMemory(name=name)
+            try:                                           # attaching must not make this process "own" the segment
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:                              # noqa: BLE001
+                pass
+        self.name = self.shm.name
+        self.owner = create
+        self.arrays = {k: np.ndarray(self.shape, dtype=dt, buffer=self.shm.buf, offset=offs[k])
+                       for k, dt in self.spec.items()}
+
+    @classmethod
+    def create_or_attach(cls, spec, shape, dist=None):
+        if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+            return cls(spec, shape)
+        rank = dist.get_rank()
+        box = [None]
+        seg = None
+        if rank == 0:
+            seg = cls(spec, shape)
+            box = [seg.name]
+        dist.broadcast_object_list(box, src=0)
+        if rank != 0:
+            seg = cls(spec, shape, name=box[0], create=False)
+        return seg
+
+    def close(self):
+        self.arrays = {}
+        if self.owner:                                     # (a mapped segment survives its unlink)
+            try:
+                self.shm.unlink()
+            except FileNotFoundError:
+                pass
+            self.owner = False
+        try:
+            self.shm.close()
+        except BufferError:                                # a view is still alive somewhere: the GC unmaps it later
+            pass
+
+
+class ShardedStackCombiner:
     """Row-band sharded combine across the ranks of ``torch.distributed`` (one process per GPU).
 
-    Every rank holds (or can read) the same N host frames, reduces only its own
-    row band (``row_band``) and the bands are gathered on rank 0; there is no
-    data-path collective because each output pixel depends only on the same
-    pixel of the N frames.  ``reduce_band(list_of_band_arrays)
-    -> dict`` defaults to the GPU ``HostStackCombiner``; tests inject the CPU
-    oracle to exercise this host logic under the ``gloo`` backend.
+    Every rank constructs one with the same arguments.  ``combine(band_frames)`` takes THIS rank's row
+    band ``[r0, r1)`` of the N host frames (``band_rows()``; a rank never needs the other rows), uploads
+    and reduces it, and writes the band of the result straight into a host array shared by all ranks;
+    after the closing barrier ``result()`` is the full-frame dict on every rank (rank 0 is the one that
+    writes the master file).  ``reduce_band`` replaces the GPU ``HostStackCombiner`` in the gloo/CPU test
+    of this host logic (it gets the list of band frames and returns a dict of band arrays)."""
 
-    Returns the dict of full-frame host arrays on rank 0 and ``None`` elsewhere.
-    """
-    import torch
-    if dist is None:
-        import torch.distributed as dist
-    world = dist.get_world_size() if dist.is_initialized() else 1
-    rank = dist.get_rank() if dist.is_initialized() else 0
+    def __init__(self, n, h, w, dist=None, reduce_band=None, out_f64=False, want_nrej=True, want_uncert=False,
+                 want_allmasked=False, dtype=np.float32, **combine_kw):
+        if dist is None:
+            import torch.distributed as dist
+        self.dist = dist
+        self.live = dist.is_initialized()
+        self.world = dist.get_world_size() if self.live else 1
+        self.rank = dist.get_rank() if self.live else 0
+        self.n, self.h, self.w = int(n), int(h), int(w)
+        self.r0, self.r1, _, _ = row_band(self.h, self.world, self.rank)
+        np_odt = np.float64 if out_f64 else np.float32
+        spec = {"data": np_odt}
+        if want_nrej:
+            spec["nrej"] = np.uint8 if self.n <= 255 else np.uint16
+        if want_uncert:
+            spec["uncert"] = np_odt
+        if want_allmasked:
+            spec["allmasked"] = np.uint8
+        self.shared = SharedHostArrays.create_or_attach(spec, (self.h, self.w), dist)
+        self.bands = {k: a[self.r0:self.r1] for k, a in self.shared.arrays.items()}
+        self.reduce_band = reduce_band
+        self.comb = None
+        self._regs = []
+        if reduce_band is None and self.r1 > self.r0:
+            torch = _native.require_cuda()
+            self._regs = [_HostRegistration(torch, a) for a in self.bands.values()]
+            self.comb = HostStackCombiner(self.n, self.r1 - self.r0, self.w, out_f64=out_f64, want_nrej=want_nrej,
+                                          want_uncert=want_uncert, want_allmasked=want_allmasked, dtype=dtype,
+                                          host_out=self.bands, **combine_kw)
+        self.h2d_bytes = self.comb.h2d_bytes if self.comb else 0
+        self.d2h_bytes = self.comb.d2h_bytes if self.comb else 0
+
+    def band_rows(self):
+        return self.r0, self.r1
+
+    def combine(self, band_frames, barrier=True):
+        if self.r1 > self.r0:
+            if self.comb is not None:
+                self.comb.combine(band_frames)
+            else:
+                res = self.reduce_band(band_frames)
+                for k, dst in self.bands.items():
+                    dst[...] = res[k]
+        if barrier and self.live:
+            self.dist.barrier()
+        return self.result()
+
+    def result(self):
+        return dict(self.shared.arrays)
+
+    def close(self):
+        for r in self._regs:
+            r.close()
+        self._regs = []
+        self.comb = None
+        self.bands = {}
+        if self.live:
+            self.dist.barrier()                 # nobody unlinks while another rank still reads
+        self.shared.close()
+
+
+def combine_sharded(frames, reduce_band=None, dist=None, **combine_kw):
+    """Convenience wrapper: every rank holds (or can read) the same N host frames; the full-frame result
+    dict (copies) is returned on rank 0 and ``None`` elsewhere."""
     n = len(frames)
     h, w = frames[0].shape
-    r0, r1, _, _ = row_band(h, world, rank)
-    bands = [np.ascontiguousarray(f[r0:r1]) for f in frames]
-    if reduce_band is None:
-        def reduce_band(bs):
-            comb = HostStackCombiner(n, r1 - r0, w, **combine_kw)
-            return {k: np.array(v, copy=True) for k, v in comb.combine(bs).items()}
-    local = reduce_band(bands) if r1 > r0 else {}
-    if world == 1:
-        return local
-    max_rows = (h + world - 1) // world
-    keys = sorted(local.keys()) if r1 > r0 else None
-    key_lists = [None] * world
-    dist.all_gather_object(key_lists, (keys, {k: str(local[k].dtype) for k in (keys or [])}))
-    keys, dtypes = next(kl for kl in key_lists if kl[0] is not None)
-    backend = dist.get_backend()
-    device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
-    out = {} if rank == 0 else None
-    for k in keys:
-        dt = np.dtype(dtypes[k])
-        pad = np.zeros((max_rows, w), dtype=dt)
-        if r1 > r0:
-            pad[: r1 - r0] = local[k]
-        t = torch.from_numpy(pad.view(np.uint8).reshape(max_rows, w * dt.itemsize)).to(device)   # raw bytes: any dtype, any backend
-        recv = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
-        dist.gather(t, recv, dst=0)
-        if rank == 0:
-            full = np.empty((h, w), dtype=dt)
-            for rk in range(world):
-                a0, a1, _, _ = row_band(h, world, rk)
-                part = recv[rk].cpu().numpy().view(dt).reshape(max_rows, w)
-                full[a0:a1] = part[: a1 - a0]
-            out[k] = full
+    sc = ShardedStackCombiner(n, h, w, dist=dist, reduce_band=reduce_band, dtype=frames[0].dtype, **combine_kw)
+    r0, r1 = sc.band_rows()
+    res = sc.combine([f[r0:r1] for f in frames])
+    out = {k: np.array(v, copy=True) for k, v in res.items()} if sc.rank == 0 else None
+    sc.close()
     return out

@@ -174,22 +174,32 @@ def run_reference(args, shape):
     dt = time.perf_counter() - t0
     mpf = n * rows * w / 1e6
     value = mpf * args.steps / dt
-    sample = f"{n} frames x {rows} rows x {w} cols per step ({mpf:.1f} Mpix-frames), numpy oracle port, {cores} threads over row bands"
+    sample = (f"{n} frames x {rows} rows x {w} cols per step ({mpf:.1f} Mpix-frames = {100.0 * rows / h:.2f} % of the frame, "
+              f"scaled), numpy oracle port, {cores} threads over row bands")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpix-frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": workload_name(shape), **{k: v for k, v in HEADLINE.items()}, "l2": "inputs >> L2"},
+        "config": bench_config(shape), "threads": cores, "rows_per_step": rows,
         "cpu_baseline": {"value": value, "unit": "Mpix-frames/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Mpix-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
+def bench_config(shape):
+    """The ``config`` object, identical in the GPU arm and the reference arm (the driver compares them)."""
+    return {"workload": workload_name(shape), **HEADLINE,
+            "l2": "inputs (24.5 GB per GPU) >> L2 (126 MB): no flush needed",
+            "reference_arm": "numpy oracle port of ccdproc.combine / astropy.sigma_clip (oracle/combine_oracle.py), "
+                             "all host threads over row bands, 4 rows per thread per step, scaled to the full frame"}
+
+
 def recorded_traffic(kname, shape):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (or None)."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    """DRAM bytes per launch of the dominant kernel from THIS round's ncu capture (profiles/r02_traffic.json,
+    refreshed with the capture); None when this kernel / shape has no capture -- never a stale constant."""
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
     try:
         with open(path) as f:
             return json.load(f)["traffic_bytes"].get(f"{kname}@{shape['n']}x{shape['h']}x{shape['w']}")
@@ -309,6 +319,18 @@ def run_gpu(args, shape):
                     lambda: kernels.stack_reduce(cube, out=out, prefer="registers_tma", **HEADLINE), n * mpix, alg_bytes)
         add_variant("stack_kappa_sigma_shared[%s]" % kernels.stack_kernel_name(n, prefer="shared", **HEADLINE),
                     lambda: kernels.stack_reduce(cube, out=out, prefer="shared", **HEADLINE), n * mpix, alg_bytes)
+        add_variant("stack_median_with_mad_uncertainty[%s]" % kernels.stack_kernel_name(n, want_uncert=True, **med),
+                    lambda: kernels.stack_reduce(cube, out=out, want_nrej=False, want_uncert=True, **med), n * mpix, (4 * n + 8) * h * w)
+        # uint16 frames (what BITPIX=16 camera files hold): the same stack rounded, 2 bytes per pixel-frame
+        c16 = torch.empty((n, h, w), dtype=torch.int16, device=device)
+        for i in range(n):
+            c16[i] = cube[i].clamp(0, 65535).round().to(torch.int32).to(torch.int16)
+        u16 = c16.view(torch.uint16)
+        add_variant("stack_kappa_sigma_u16_frames[%s]" % kernels.stack_kernel_name(n, **HEADLINE),
+                    lambda: kernels.stack_reduce(u16, out=out, **HEADLINE), n * mpix, (2 * n + 5) * h * w)
+        add_variant("stack_medmad_5sigma_1pass_apmastercal_u16_frames[%s]" % kernels.stack_kernel_name(n, **ref),
+                    lambda: kernels.stack_reduce(u16, out=out, **ref), n * mpix, (2 * n + 5) * h * w)
+        del c16, u16
         for nn in (16, 30, 64, 128, 200):
             if nn > n_alloc:
                 continue
@@ -394,7 +416,93 @@ def run_gpu(args, shape):
                "steps": esteps, "ms_per_step": 1e3 * dt / esteps, "api": "pipeline.HostStackCombiner.combine",
                "host_frames_distinct": len(host_frames), "matches_device_path": same,
                "pcie_gbs": comb.h2d_bytes * esteps / dt / 1e9}
-        del comb, keep, host_frames, frames
+        del comb, keep, host_frames, frames, res
+        _release_pinned_cache(torch)
+
+    # ---- the same through uint16 host frames (raw BITPIX=16 frames: half the PCIe and HBM bytes) ----
+    e2e_u16 = None
+    if not args.no_e2e:
+        host16, keep16 = [], []
+        for i in range(min(n, n_host)):
+            arr, t = pipeline.pinned_empty((h, w), np.uint16)
+            t.view(torch.int16).copy_(cube[i].clamp(0, 65535).round().to(torch.int32).to(torch.int16))
+            host16.append(arr)
+            keep16.append(t)
+        torch.cuda.synchronize()
+        frames16 = [host16[i % len(host16)] for i in range(n)]
+        comb16 = pipeline.HostStackCombiner(n, h, w, **HEADLINE, band_bytes=2 << 30, device=device, dtype=np.uint16)
+        comb16.combine(frames16)                                 # warm-up
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(esteps):
+            comb16.combine(frames16)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e_u16 = {"value": world * n * mpix * esteps / dt, "unit": "Mpix-frames/s",
+                   "h2d_bytes_per_step": comb16.h2d_bytes, "d2h_bytes_per_step": comb16.d2h_bytes,
+                   "steps": esteps, "ms_per_step": 1e3 * dt / esteps,
+                   "api": "pipeline.HostStackCombiner.combine(dtype=uint16)",
+                   "frames": "the same frames rounded to uint16 (what a BITPIX=16 camera file holds)",
+                   "pcie_gbs": comb16.h2d_bytes * esteps / dt / 1e9}
+        del comb16, keep16, host16, frames16
+        _release_pinned_cache(torch)
+
+    # ---- strong scaling: ONE stack of BASELINE config 4 (200 frames of 9576x6388 float32) row-sharded over the
+    # ranks through the product API; every rank uploads only its band, the result lands in one shared host array ----
+    strong = None
+    if not args.no_strong:
+        ns = 200 if not args.small else 24
+        sc = pipeline.ShardedStackCombiner(ns, h, w, dist=dist, dtype=np.float32, want_nrej=True, band_bytes=2 << 30,
+                                           **HEADLINE)
+        r0, r1 = sc.band_rows()
+        brows = r1 - r0
+        avail = _mem_available_bytes()
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+        per_frame = brows * w * 4
+        n_dist = ns
+        if avail is not None and ns * per_frame * local_world > 0.5 * avail:
+            n_dist = max(4, int(0.5 * avail / local_world / max(per_frame, 1)))
+        bands, keepb = [], []
+        for i in range(min(ns, n_dist)):
+            arr, t = pipeline.pinned_empty((brows, w), np.float32)
+            t.copy_(cube_all[i % cube_all.shape[0], r0:r1])
+            bands.append(arr)
+            keepb.append(t)
+        torch.cuda.synchronize()
+        band_frames = [bands[i % len(bands)] for i in range(ns)]
+        sc.combine(band_frames)                                   # warm-up (ends with a barrier)
+        ssteps = max(1, min(args.steps, 2))
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(ssteps):
+            sres = sc.combine(band_frames)                        # H2D of the band + reduce + D2H + barrier
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        h2d_all = ns * h * w * 4
+        full_ok = None
+        if rank == 0:
+            full_ok = bool(np.isfinite(sres["data"]).all()) and sres["data"].shape == (h, w)
+        strong = {"scaling": "strong", "workload": f"kappa-sigma-clipped mean stack {ns}x({w}x{h}) float32, rows sharded over {world} GPU(s)",
+                  "value": ns * mpix * ssteps / dt, "unit": "Mpix-frames/s", "n_gpus": world,
+                  "ms_per_step": 1e3 * dt / ssteps, "steps": ssteps,
+                  "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": 5 * h * w,
+                  "h2d_gbs_aggregate": h2d_all * ssteps / dt / 1e9, "h2d_gbs_per_gpu": h2d_all * ssteps / dt / 1e9 / world,
+                  "rows_per_rank": brows, "host_frames_distinct": len(bands), "result_complete_on_rank0": full_ok,
+                  "api": "pipeline.ShardedStackCombiner.combine (band upload, reduce, D2H into the shared host result, barrier)"}
+        del sres, band_frames, bands, keepb
+        sc.close()
+        _release_pinned_cache(torch)
 
     # ---- CPU baseline: oracle port, single thread, bounded sample (rank 0, N=1 only) ----
     cpu = None
@@ -413,17 +521,24 @@ def run_gpu(args, shape):
             "metric": METRIC, "value": value, "unit": "Mpix-frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(shape), **HEADLINE, "kernel": kname,
-                       "per_gpu": f"{n}x({w}x{h})", "l2": "inputs (24.5 GB/GPU) >> L2 (126 MB): no flush needed"},
+            "config": bench_config(shape),
+            "kernel_info": {"kernel": kname, "per_gpu": f"{n}x({w}x{h})"},
             "clocks": clocks, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": recorded_traffic(kname, shape), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel": kname},
-            "e2e": e2e, "cpu_baseline": cpu, "variants": variants,
+            "e2e": e2e, "e2e_u16": e2e_u16, "strong": strong, "cpu_baseline": cpu, "variants": variants,
         }
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def _release_pinned_cache(torch):
+    """Give cached page-locked blocks back to the OS between the host-buffer sections."""
+    fn = getattr(torch._C, "_host_emptyCache", None)
+    if fn is not None:
+        fn()
 
 
 def _mem_available_bytes():
@@ -447,6 +562,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the row-sharded 200-frame strong-scaling record")
     args = ap.parse_args()
     shape = SMALL if args.small else FULL
     if args.impl == "reference":
