@@ -1,7 +1,12 @@
 """BASELINE config 5: throughput sweep over frame count N x frame size, for the median, the reference's
-median/MAD clip, the kappa-sigma clip and calibrate-only, on one GPU (device-resident inputs).
+median/MAD clip, the kappa-sigma clip and calibrate-only (device-resident inputs).
 
     python tools/sweep.py > profiles/rNN_sweep_1gpu.md
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port P \
+        tools/sweep.py > profiles/rNN_sweep_8gpu.md
+
+Under torchrun every rank owns its row band of every frame (pipeline.row_band), the ranks start together and
+the slowest rank's CUDA-event time counts; the table holds the whole job's Mpix-frames/s.
 """
 import os, sys, json, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -22,9 +27,31 @@ MODES = {
 MAX_BYTES = 60e9
 
 
+WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+RANK = int(os.environ.get("RANK", "0"))
+dist = None
+
+
+def say(line):
+    if RANK == 0:
+        print(line, flush=True)
+
+
 def timeit(fn, reps):
     fn(); fn()
     torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+        torch.cuda.synchronize()
+    ms = _timeit(fn, reps)
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def _timeit(fn, reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
@@ -35,10 +62,24 @@ def timeit(fn, reps):
 
 
 def main():
-    g = torch.Generator(device="cuda"); g.manual_seed(5)
-    print(f"| frame | N | mode | kernel | ms | Mpix-frames/s | GB/s | of {PEAK:.0f} GB/s |")
-    print("|---|---:|---|---|---:|---:|---:|---:|")
-    for (h, w) in SIZES:
+    global dist
+    if WORLD > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        saved = os.dup(1)
+        os.dup2(2, 1)                       # NCCL announces itself on stdout
+        dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+        dist.barrier()
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+    from astrophotography_b200 import pipeline
+    g = torch.Generator(device="cuda"); g.manual_seed(5 + RANK)
+    say(f"{WORLD} GPU(s), rows of every frame sharded over the ranks; fractions are per GPU, of {PEAK:.0f} GB/s\n")
+    say(f"| frame | N | mode | kernel | ms | Mpix-frames/s (all GPUs) | GB/s per GPU | of {PEAK:.0f} GB/s |")
+    say("|---|---:|---|---|---:|---:|---:|---:|")
+    for (hfull, w) in SIZES:
+        r0, r1, _, _ = pipeline.row_band(hfull, WORLD, RANK)
+        h = r1 - r0
         nmax = max(n for n in NS if n * h * w * 4 <= MAX_BYTES)
         cube = torch.empty((nmax, h, w), dtype=torch.float32, device="cuda")
         for i in range(nmax):
@@ -54,16 +95,18 @@ def main():
                 ms = timeit(lambda: kernels.stack_reduce(sub, out=out, **kw), 3 if n * h * w > 2e9 else 10)
                 nbytes = (4 * n + (4 if mode == "median" else 5)) * h * w
                 name = kernels.stack_kernel_name(n, **{k: v for k, v in kw.items() if k != "want_nrej"})
-                print(f"| {w}x{h} | {n} | {mode} | {name}/{kernels.stack_last_staging()} | {ms:.3f} | "
-                      f"{n * h * w / ms / 1e3:.0f} | {nbytes / ms / 1e6:.0f} | {nbytes / ms / 1e6 / PEAK:.2f} |")
+                say(f"| {w}x{hfull} | {n} | {mode} | {name}/{kernels.stack_last_staging()} | {ms:.3f} | "
+                    f"{n * hfull * w / ms / 1e3:.0f} | {nbytes / ms / 1e6:.0f} | {nbytes / ms / 1e6 / PEAK:.2f} |")
         # calibrate-only
         raw, bias, dark, flat = cube[0], cube[1], cube[2], cube[3].abs() + 1.0
         cal = torch.empty((h, w), dtype=torch.float32, device="cuda")
         ms = timeit(lambda: kernels.calibrate(raw, bias, dark, flat, 1.0 / 3.0, True, out=cal), 20)
-        print(f"| {w}x{h} | 1 | calibrate-only (f32 raw) | calibrate_vec4 | {ms:.4f} | {h * w / ms / 1e3:.0f} | "
-              f"{20 * h * w / ms / 1e6:.0f} | {20 * h * w / ms / 1e6 / PEAK:.2f} |")
+        say(f"| {w}x{hfull} | 1 | calibrate-only (f32 raw) | calibrate_vec4 | {ms:.4f} | {hfull * w / ms / 1e3:.0f} | "
+            f"{20 * h * w / ms / 1e6:.0f} | {20 * h * w / ms / 1e6 / PEAK:.2f} |")
         del cube, sub
         torch.cuda.empty_cache()
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
