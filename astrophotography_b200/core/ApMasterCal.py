@@ -203,6 +203,7 @@ class ApMasterCal(ApBase):
         return kw
 
     def _load_frames(self):
+        """The frames as float32 host arrays (array-level users; ``make_master`` streams the files instead)."""
         frames = []
         for path in self._files.files_filtered(include_path=True):
             data, _hdr = fitsio.read_image(path, 0)
@@ -214,16 +215,39 @@ class ApMasterCal(ApBase):
         return frames
 
     def combine_frames(self, frames):
-        """Combine in-memory (H,W) float32 frames with this object's settings.
-        Returns the dict of host arrays ``data, nrej, uncert, allmasked``."""
+        """Combine in-memory (H,W) frames (float32, or uint16 raw frames) with this object's settings.
+        Returns the dict of host arrays ``data, nrej, uncert, allmasked``.  The double-buffered combiner
+        (device buffers, pinned result planes) is kept and reused while the stack geometry stays the same."""
         n = len(frames)
         h, w = frames[0].shape
-        comb = pipeline.HostStackCombiner(n, h, w, out_f64=self._out_f64, want_nrej=True, want_uncert=True,
-                                          want_allmasked=True, **self._combine)
-        res = comb.combine(frames)
+        dtype = np.dtype(frames[0].dtype)
+        key = (n, h, w, dtype.str)
+        if getattr(self, "_combiner_key", None) != key:
+            self._combiner = pipeline.HostStackCombiner(n, h, w, out_f64=self._out_f64, want_nrej=True, want_uncert=True,
+                                                        want_allmasked=True, dtype=dtype, **self._combine)
+            self._combiner_key = key
+        res = self._combiner.combine(frames)
         return {k: np.array(v, copy=True) for k, v in res.items()}
 
-    def make_master(self, output_master_file):
+    def combine_files(self, gpus=1):
+        """Combine the files of this object's collection: every file is read once, straight into page-locked
+        memory, while the previous frames upload (raw BITPIX=16 frames travel undecoded, 2 bytes per pixel);
+        ``gpus > 1`` shards the rows over that many GPUs of this box (one process each)."""
+        paths = self._files.files_filtered(include_path=True)
+        opts = dict(out_f64=self._out_f64, want_nrej=True, want_uncert=True, want_allmasked=True, **self._combine)
+        try:
+            if gpus and int(gpus) > 1:
+                return pipeline.combine_files_sharded(paths, int(gpus), **opts)
+            src = pipeline.FileFrames(paths, fitsio)
+            self._logger.debug(f"Streaming {src.n} frames of {src.w}x{src.h} as {src.dtype} ({src.u16_format}).")
+            res = pipeline.combine_files(src, **opts)
+        except RuntimeError as exc:
+            if "not a 2-D image" in str(exc) or "has shape" in str(exc):
+                self._logger.error(str(exc))
+            raise
+        return {k: np.array(v, copy=True) for k, v in res.items()}
+
+    def make_master(self, output_master_file, gpus=1):
         """Combine the raw calibration files into a master file and write it."""
         kw_dict = self._generate_final_keywords()
         cal_type = kw_dict["IMAGETYP"][0]
@@ -231,8 +255,7 @@ class ApMasterCal(ApBase):
         c = self._combine
         self._logger.debug(f"About to combine {nfiles} {cal_type} files, method={c['method']} sigma_clip={c['maxiters'] != 0}"
                            f" sig_clip_lothresh={c['k_lo']} sig_clip_hithresh={c['k_hi']}.")
-        frames = self._load_frames()
-        res = self.combine_frames(frames)
+        res = self.combine_files(gpus)
         first = self._files.files_filtered(include_path=True)[0]
         hdr = fitsio.read_header(first, 0).copy()
         # PEDESTAL stays, as in the reference: ccdproc.combine never applies it to the frames and keeps the

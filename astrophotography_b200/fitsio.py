@@ -363,6 +363,54 @@ def read_header(path, ext=0):
     return _mini_read(str(path), ext, header_only=True)[1]
 
 
+class ImageLayout:
+    """Where the pixels of a 2-D image HDU sit in its file, so that a row band can be read straight into
+    page-locked memory (one ``readinto``, no parsing, no intermediate array)."""
+
+    def __init__(self, path, ext=0):
+        self.path = str(path)
+        with open(self.path, "rb") as f:
+            for hdu in range(ext + 1):
+                hdr = _read_header_block(f)
+                nbytes, shape = _data_nbytes(hdr)
+                if hdu < ext:
+                    f.seek((nbytes + BLOCK - 1) // BLOCK * BLOCK, os.SEEK_CUR)
+            self.offset = f.tell()
+        self.header = hdr
+        self.shape = shape
+        self.bitpix = int(hdr["BITPIX"])
+        self.bzero = hdr.get("BZERO", 0) or 0
+        self.bscale = hdr.get("BSCALE", 1) or 1
+        self.itemsize = abs(self.bitpix) // 8
+
+    @property
+    def raw_u16(self):
+        """BITPIX=16 with BZERO=32768: the data unit can go to ``apgpu_stack_reduce_u16`` /
+        ``apgpu_calibrate_u16`` as it is on disk (``u16_format='fits'``)."""
+        return len(self.shape) == 2 and self.bitpix == 16 and self.bscale == 1 and self.bzero == 32768
+
+    def same_pixels_as(self, other):
+        return (self.shape, self.bitpix, self.bzero, self.bscale) == (other.shape, other.bitpix, other.bzero, other.bscale)
+
+    def read_rows_raw(self, r0, r1, out):
+        """Rows ``[r0, r1)`` exactly as stored (big-endian) into ``out``, a C-contiguous array of
+        ``(r1 - r0) * NAXIS1 * itemsize`` bytes of any dtype."""
+        w = self.shape[1]
+        buf = memoryview(out).cast("B")
+        want = (r1 - r0) * w * self.itemsize
+        if buf.nbytes != want:
+            raise ValueError(f"read_rows_raw: buffer of {buf.nbytes} bytes for {want} bytes of pixels")
+        with open(self.path, "rb", buffering=0) as f:
+            f.seek(self.offset + r0 * w * self.itemsize)
+            got = 0
+            while got < want:
+                k = f.readinto(buf[got:])
+                if not k:
+                    raise OSError(f"truncated FITS data unit in {self.path}")
+                got += k
+        return out
+
+
 def new_header(cards=None):
     if HAVE_ASTROPY:
         h = _afits.Header()

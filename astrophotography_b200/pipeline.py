@@ -224,7 +224,7 @@ class SharedHostArrays:
     name through ``torch.distributed``); ``arrays[key]`` are numpy views.  The creating process unlinks
     the segment on ``close``."""
 
-    def __init__(self, spec, shape, name=None, create=True):
+    def __init__(self, spec, shape, name=None, create=True, shared_tracker=False):
         from multiprocessing import shared_memory
         self.spec = {k: np.dtype(v) for k, v in spec.items()}
         self.shape = tuple(shape)
@@ -239,11 +239,15 @@ class SharedHostArrays:
             self.shm = shared_memory.SharedMemory(create=True, size=total)
         else:
             self.shm = shared_memory.SharedMemory(name=name)
-            try:                                           # attaching must not make this process "own" the segment
-                from multiprocessing import resource_tracker
-                resource_tracker.unregister(self.shm._name, "shared_memory")
-            except Exception:                              # noqa: BLE001
-                pass
+            # Python < 3.13 registers a segment with the resource tracker on attach as well: an independent
+            # process (torchrun rank) must take that back or its tracker unlinks the segment at exit; a child
+            # spawned by the creator shares the creator's tracker, where the name is registered once anyway
+            if not shared_tracker:
+                try:
+                    from multiprocessing import resource_tracker
+                    resource_tracker.unregister(self.shm._name, "shared_memory")
+                except Exception:                          # noqa: BLE001
+                    pass
         self.name = self.shm.name
         self.owner = create
         self.arrays = {k: np.ndarray(self.shape, dtype=dt, buffer=self.shm.buf, offset=offs[k])
@@ -347,6 +351,154 @@ class ShardedStackCombiner:
         if self.live:
             self.dist.barrier()                 # nobody unlinks while another rank still reads
         self.shared.close()
+
+
+# ---------------------------------------------------------------------------
+# files -> master: read each frame once, straight into page-locked memory, while the previous ones upload
+# ---------------------------------------------------------------------------
+class FileFrames:
+    """The N frames of a stack as FITS files (``fitsio.ImageLayout`` each).  When every file is a BITPIX=16 /
+    BZERO=32768 image (raw camera frames, reference doc/fits_metadata.md:70-76) the data units travel to the GPU
+    as they are on disk (``u16_format='fits'``: 2 bytes per pixel, no host conversion); anything else is read
+    through ``fitsio.read_image`` and converted to float32 on the host like the reference's ``_read_fits``."""
+
+    def __init__(self, paths, fitsio):
+        self.fitsio = fitsio
+        self.paths = [str(p) for p in paths]
+        self.layouts = [fitsio.ImageLayout(p) for p in self.paths]
+        for p, lay in zip(self.paths, self.layouts):
+            if len(lay.shape) != 2:
+                raise RuntimeError(f"Error, {p} is not a 2-D image.")
+            if lay.shape != self.layouts[0].shape:
+                raise RuntimeError(f"Error, {p} has shape {lay.shape}, expected {self.layouts[0].shape}.")
+        self.n = len(self.paths)
+        self.h, self.w = self.layouts[0].shape
+        self.raw_u16 = all(lay.raw_u16 for lay in self.layouts)
+        self.dtype = np.dtype(np.uint16 if self.raw_u16 else np.float32)
+        self.u16_format = "fits" if self.raw_u16 else "native"
+
+    def read_band(self, i, r0, r1, out):
+        """Rows ``[r0, r1)`` of frame ``i`` into ``out`` (a (r1-r0, W) array of ``self.dtype``)."""
+        if self.raw_u16:
+            self.layouts[i].read_rows_raw(r0, r1, out)
+        else:
+            data, _ = self.fitsio.read_image(self.paths[i], 0)
+            out[...] = data[r0:r1]               # numpy converts to float32 (reference: data.astype(np.float32))
+
+
+def combine_files(src, r0=0, r1=None, host_out=None, out_f64=False, want_nrej=True, want_uncert=False,
+                  want_allmasked=False, device=None, hbm_fraction=0.6, ring=3, **params):
+    """Rows ``[r0, r1)`` of the combined master of the files in ``src`` (a ``FileFrames``).
+
+    Frame ``i+1`` is read from its file (``readinto`` page-locked staging memory) while frame ``i`` travels to
+    the device cube; one ``stack_reduce`` launch follows and the result planes come back into ``host_out``
+    (arrays of shape ``(r1-r0, W)``; pinned arrays of this call by default).  Stacks larger than
+    ``hbm_fraction`` of the free HBM are reduced in row bands, re-reading the files once per band."""
+    torch = _native.require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    n, w = src.n, src.w
+    r1 = src.h if r1 is None else r1
+    rows = r1 - r0
+    item = src.dtype.itemsize
+    np_odt = np.float64 if out_f64 else np.float32
+    spec = {"data": np_odt}
+    if want_nrej:
+        spec["nrej"] = np.uint8 if n <= 255 else np.uint16
+    if want_uncert:
+        spec["uncert"] = np_odt
+    if want_allmasked:
+        spec["allmasked"] = np.uint8
+    keep = []
+    if host_out is None:
+        host_out = {}
+        for k, dt in spec.items():
+            arr, t = pinned_empty((rows, w), dt)
+            host_out[k] = arr
+            keep.append(t)
+    free_b, _total = torch.cuda.mem_get_info(dev)
+    band = int(max(1, min(rows, hbm_fraction * free_b // (n * w * item + 40 * w))))
+    if band < rows and src.raw_u16:
+        step = 8 // int(np.gcd(8, w))
+        band = max(step, band - band % step)
+    cdt = torch.float32 if src.dtype == np.float32 else torch.int16
+    cube = torch.empty((n, band, w), dtype=cdt, device=dev)
+    outs = {k: torch.empty((band, w), dtype=_torch_dtype(torch, dt) if np.dtype(dt) != np.uint16 else torch.uint16, device=dev)
+            for k, dt in spec.items()}
+    stage = [pinned_empty((band, w), src.dtype) for _ in range(ring)]
+    free_ev = [None] * ring
+    copy_stream = torch.cuda.Stream(device=dev)
+    for b0 in range(0, rows, band):
+        b1 = min(rows, b0 + band)
+        nb = b1 - b0
+        for i in range(n):
+            slot = i % ring
+            if free_ev[slot] is not None:
+                free_ev[slot].synchronize()          # the upload that last used this staging buffer is done
+            arr, t = stage[slot]
+            src.read_band(i, r0 + b0, r0 + b1, arr[:nb])
+            with torch.cuda.stream(copy_stream):
+                cube[i, :nb].copy_(host_tensor(torch, arr)[:nb] if t.dtype == torch.uint16 else t[:nb], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                free_ev[slot] = ev
+        torch.cuda.current_stream().wait_stream(copy_stream)
+        kernels.stack_reduce(cube, row0=0, nrows=nb, out=outs, u16_format=src.u16_format, out_f64=out_f64,
+                             want_nrej=want_nrej, want_uncert=want_uncert, want_allmasked=want_allmasked, **params)
+        for k in spec:
+            dst = host_tensor(torch, host_out[k])[b0:b1]
+            s_ = outs[k][:nb]
+            dst.copy_(s_.view(dst.dtype) if dst.dtype != s_.dtype else s_, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    return host_out
+
+
+def _file_shard_worker(rank, world, seg_name, spec, paths, opts, devices):
+    """One process per GPU of ``combine_files_sharded``: rows ``row_band(H, world, rank)`` of every file."""
+    import torch
+    from . import fitsio
+    torch.cuda.set_device(devices[rank])
+    src = FileFrames(paths, fitsio)
+    seg = SharedHostArrays(spec, (src.h, src.w), name=seg_name, create=False, shared_tracker=True)
+    r0, r1, _, _ = row_band(src.h, world, rank)
+    if r1 > r0:
+        bands = {k: a[r0:r1] for k, a in seg.arrays.items()}
+        regs = [_HostRegistration(torch, a) for a in bands.values()]
+        combine_files(src, r0, r1, host_out=bands, **opts)
+        for reg in regs:
+            reg.close()
+        del bands
+    seg.close()
+
+
+def combine_files_sharded(paths, gpus, out_f64=False, want_nrej=True, want_uncert=False, want_allmasked=False,
+                          devices=None, **params):
+    """``combine_files`` over ``gpus`` GPUs of this box: one spawned process per GPU reads and reduces its row band
+    of every file and writes it into a shared host array; returns the full-frame dict (copies).  ``devices``
+    (tests): the CUDA device index of every rank, default ``range(gpus)``."""
+    import torch
+    import torch.multiprocessing as mp
+    from . import fitsio
+    devices = list(range(gpus)) if devices is None else list(devices)
+    if len(devices) != gpus or max(devices) >= torch.cuda.device_count():
+        raise RuntimeError(f"combine_files_sharded: {gpus} GPUs requested, {torch.cuda.device_count()} visible")
+    lay = fitsio.ImageLayout(paths[0])
+    n = len(paths)
+    np_odt = np.float64 if out_f64 else np.float32
+    spec = {"data": np_odt}
+    if want_nrej:
+        spec["nrej"] = np.uint8 if n <= 255 else np.uint16
+    if want_uncert:
+        spec["uncert"] = np_odt
+    if want_allmasked:
+        spec["allmasked"] = np.uint8
+    seg = SharedHostArrays(spec, lay.shape)
+    try:
+        opts = dict(out_f64=out_f64, want_nrej=want_nrej, want_uncert=want_uncert, want_allmasked=want_allmasked, **params)
+        mp.spawn(_file_shard_worker, args=(gpus, seg.name, {k: np.dtype(v).str for k, v in spec.items()},
+                                           [str(p) for p in paths], opts, devices), nprocs=gpus, join=True)
+        return {k: np.array(v, copy=True) for k, v in seg.arrays.items()}
+    finally:
+        seg.close()
 
 
 def combine_sharded(frames, reduce_band=None, dist=None, **combine_kw):

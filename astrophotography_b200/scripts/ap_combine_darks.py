@@ -37,6 +37,8 @@ def command_line_opts(argv):
     parser.add_argument("--cenfunc", default="median", choices=["median", "mean"])
     parser.add_argument("--devfunc", default="mad_std", choices=["mad_std", "std"])
     parser.add_argument("--out_dtype", default="float64", choices=["float64", "float32"])
+    parser.add_argument("--gpus", type=int, default=1,
+                        help="Shard the rows of the stack over this many GPUs of the box (one process each). Default: 1")
     return parser.parse_args(argv)
 
 
@@ -48,7 +50,7 @@ def main(args=None):
                             method=p.method, sigma_clip=not p.no_sigma_clip,
                             sigma_clip_low_thresh=p.kappa_low, sigma_clip_high_thresh=p.kappa_high,
                             maxiters=p.maxiters, cenfunc=p.cenfunc, devfunc=p.devfunc, out_dtype=p.out_dtype)
-        mkcal.make_master(p.master_filename)
+        mkcal.make_master(p.master_filename, gpus=p.gpus)
     except RuntimeError as rte:
         logger.error(f"Shutting down due to exception raised by ApMasterCal: {rte}")
         return 1

@@ -172,6 +172,86 @@ def test_apmastercal_make_master(cuda, tmp_path):
     assert med.dtype == np.float32 and np.array_equal(med, np.median(st.astype(np.float64), axis=0).astype(np.float32))
 
 
+def _write_dark_files(d, n, shape, as_u16=True):
+    from astrophotography_b200 import fitsio, synth
+    st = synth.dark_stack(n, shape, exptime=300.0, quantise=True)
+    d.mkdir()
+    for k in range(n):
+        hdr = fitsio.new_header({"IMAGETYP": "Dark Frame", "EXPTIME": 300.0, "SET-TEMP": -20.0, "CCD-TEMP": -20.0, "TELESCOP": "T5"})
+        fitsio.write_image(d / f"d{k:03d}.fits", st[k].astype(np.uint16) if as_u16 else st[k], hdr)
+    return st
+
+
+@pytest.mark.parametrize("as_u16", [True, False])
+def test_make_master_streams_files_and_shards_rows(cuda, tmp_path, as_u16):
+    """make_master reads every file once into page-locked memory while the previous frames upload (raw BITPIX=16
+    data units travel undecoded); ``gpus=2`` shards the rows over two worker processes (both on cuda:0 here) that
+    write into one shared host array.  Same master either way, equal to the oracle."""
+    from astrophotography_b200 import ApMasterCal, fitsio, pipeline
+    from oracle import combine_oracle as C
+    n, shape = 12, (45, 72)
+    st = _write_dark_files(tmp_path / "darks", n, shape, as_u16)
+    exp = C.combine(st, "average", 5.0, 5.0, 1, "median", "mad_std")
+    mc = ApMasterCal(str(tmp_path / "darks"), "master*", "T5", 0.5, "ERROR")
+    src = pipeline.FileFrames(mc._files.files_filtered(include_path=True), fitsio)
+    assert src.raw_u16 == as_u16 and src.u16_format == ("fits" if as_u16 else "native")
+    one = mc.combine_files()
+    opts = dict(out_f64=True, want_nrej=True, want_uncert=True, want_allmasked=True, **mc._combine)
+    two = pipeline.combine_files_sharded(src.paths, 2, devices=[0, 0], **opts)
+    for res in (one, two):
+        assert np.array_equal(res["nrej"].astype(np.int64), exp["nrej"])
+        assert np.allclose(res["data"], exp["data"], rtol=1e-13, atol=0)
+        assert np.allclose(res["uncert"], exp["uncert"], rtol=1e-10, atol=1e-12)
+    assert np.array_equal(one["data"], two["data"])
+    if torch_device_count() >= 2:
+        mc.make_master(str(tmp_path / "m2.fits"), gpus=2)
+        data, _ = fitsio.read_image(tmp_path / "m2.fits", 0)
+        assert np.array_equal(data, one["data"])
+
+
+def torch_device_count():
+    import torch
+    return torch.cuda.device_count()
+
+
+def test_make_master_overlaps_file_reads_with_uploads(cuda, tmp_path):
+    """30 x 4096^2 raw uint16 files (BASELINE config 2's master): streaming the files through combine_files must
+    cost no more than 1.3 x (reading them + combining pre-pinned arrays); the numbers are printed."""
+    import time
+    import torch
+    from astrophotography_b200 import fitsio, pipeline
+    n, shape = 30, (4096, 4096)
+    d = tmp_path / "big"
+    d.mkdir()
+    rng = np.random.default_rng(1)
+    base = rng.normal(1000, 12, shape).astype(np.float32)
+    for k in range(n):
+        fr = np.clip(np.rint(base + rng.normal(0, 12, shape).astype(np.float32)), 0, 65535).astype(np.uint16)
+        fitsio.write_image(d / f"b{k:02d}.fits", fr, fitsio.new_header({"IMAGETYP": "Bias Frame"}))
+    paths = sorted(str(p) for p in d.iterdir())
+    src = pipeline.FileFrames(paths, fitsio)
+    assert src.raw_u16
+    params = dict(method="average", k_lo=5.0, k_hi=5.0, maxiters=1, cen="median", dev="mad_std")
+    pipeline.combine_files(src, **params)                                  # warm-up (page cache, CUDA context)
+    t0 = time.perf_counter()
+    res = pipeline.combine_files(src, **params)
+    t_files = time.perf_counter() - t0
+    pinned = [pipeline.pinned_empty(shape, np.uint16) for _ in range(n)]
+    t0 = time.perf_counter()
+    for i in range(n):
+        src.read_band(i, 0, shape[0], pinned[i][0])
+    t_read = time.perf_counter() - t0
+    comb = pipeline.HostStackCombiner(n, shape[0], shape[1], dtype=np.uint16, u16_format="fits", **params)
+    comb.combine([p[0] for p in pinned])
+    t0 = time.perf_counter()
+    ref = comb.combine([p[0] for p in pinned])
+    torch.cuda.synchronize()
+    t_comb = time.perf_counter() - t0
+    print(f"combine_files {t_files * 1e3:.1f} ms; read only {t_read * 1e3:.1f} ms; pre-pinned HostStackCombiner {t_comb * 1e3:.1f} ms")
+    assert np.array_equal(res["data"], ref["data"]) and np.array_equal(res["nrej"], ref["nrej"])
+    assert t_files <= 1.3 * (t_read + t_comb)
+
+
 def test_master_keeps_pedestal_and_apcalibrate_removes_it(cuda, tmp_path):
     """MaximDL-style frames carry PEDESTAL=-100.  Like ccdproc.combine the master keeps the keyword (the
     frames are combined as stored) and ApCalibrate._read_fits removes the pedestal from the master bias /
