@@ -60,6 +60,7 @@ SOURCES = ['stack_sorted_med_f32_p3.cu',
            'stack.cu',
            'apgpu_core.cu',
            'calibrate.cu',
+           'calibrate_repair.cu',
            'badpix.cu',
            'stats.cu']
 NVCC_FLAGS = [
@@ -82,6 +83,7 @@ def _nvcc() -> str:
 def _digest(paths) -> str:
     h = hashlib.sha256()
     h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(SOURCES).encode())
     for p in sorted(paths):
         with open(p, "rb") as f:
             h.update(p.encode())

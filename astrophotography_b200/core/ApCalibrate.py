@@ -201,6 +201,126 @@ class ApCalibrate(ApBase):
             return img, odict
         return img.cpu().numpy(), odict
 
+    def _base_odict(self):
+        odict = {"BIASCORR": (True, "True if bias subtracted."),
+                 "BIASFILE": (self._master_bias.name, "Master bias file used."),
+                 "DARKCORR": (True, "True if scaled dark subtracted."),
+                 "DARKFILE": (self._master_dark.name, "Master dark file used."),
+                 "BUNIT": ("adu", "Pixel value units.")}
+        if self._norm_flat_dev is not None:
+            odict["FLATCORR"] = (True, "True if flat field applied.")
+            odict["FLATFILE"] = (self._master_flat.name, "Master flat file used.")
+        return odict
+
+    # -- batch driver (additive; replaces scripts/calibrate_all.sh:353-480) --------------------------------
+    def calibrate_many(self, raw_images, cal_images, delta_pix=2, ring=3):
+        """Calibrate many frames with ONE set of device-resident masters.
+
+        The reference's batch driver starts one Python process per frame (``calibrate_all.sh:406-411``), each
+        re-reading the four masters.  Here frame ``k+1`` is read from its file into page-locked memory (raw
+        BITPIX=16 data units undecoded: 2 bytes per pixel over PCIe) and uploaded on a copy stream while frame
+        ``k`` runs through ONE fused calibrate + repair launch and frame ``k-1`` returns on a third stream --
+        already in FITS byte order, so writing the output is the header plus one ``write`` of the pinned buffer.
+        Output files equal those of ``calibrate(raw, cal, delta_pix, None, False)`` pixel for pixel.
+        Returns the list of per-frame keyword dictionaries."""
+        from .. import fitsio, pipeline
+        torch = self._torch
+        raw_images = [Path(p) for p in raw_images]
+        cal_images = [Path(p) for p in cal_images]
+        if len(raw_images) != len(cal_images):
+            raise RuntimeError("calibrate_many: one output name per raw frame is needed")
+        shape = tuple(self._bias_dev.shape)
+        h, w = shape
+        mask_u8 = None
+        if self._bpix is not None:
+            mask_u8 = self._mask_dev if self._mask_dev.dtype == torch.uint8 else (self._mask_dev != 0).to(torch.uint8)
+        if self._dark_still_biased:
+            self._logger.info("Subtracting bias from dark")
+        copy_s, comp_s, back_s = (torch.cuda.Stream(device=self._device) for _ in range(3))
+        slots = []
+        for _ in range(ring):
+            u16_np, u16_t = pipeline.pinned_empty(shape, np.uint16)
+            f32_np, f32_t = pipeline.pinned_empty(shape, np.float32)
+            out_np, out_t = pipeline.pinned_empty(shape, np.float32)
+            slots.append(dict(u16_np=u16_np, u16_t=u16_t.view(torch.int16), f32_np=f32_np, f32_t=f32_t, out_np=out_np, out_t=out_t,
+                              raw16=torch.empty(shape, dtype=torch.int16, device=self._device),
+                              raw32=torch.empty(shape, dtype=torch.float32, device=self._device),
+                              out=torch.empty(shape, dtype=torch.float32, device=self._device),
+                              counts=torch.zeros(2, dtype=torch.int64, device=self._device),
+                              counts_host=torch.zeros(2, dtype=torch.int64).pin_memory(),
+                              done=None, pending=None, consumed=None))
+        results = [None] * len(raw_images)
+
+        def finish(slot):
+            if slot["pending"] is None:
+                return
+            idx, hdr, odict, t0 = slot["pending"]
+            slot["done"].synchronize()
+            if mask_u8 is not None:
+                nbad, nfixed = (int(v) for v in slot["counts_host"].tolist())
+                odict["BPIXFILE"] = (self._master_bpix.name, "Name of master bad pixel file used")
+                for key, val in self._bpix._stats_dict(h * w, nbad, nfixed, int(delta_pix)).items():
+                    if "BPIX" in key:
+                        odict[key] = val
+            out_hdr = self._header_like(hdr, odict, f"Processed by {self._name}")
+            fitsio.write_data_unit(cal_images[idx], slot["out_np"], -32, shape, out_hdr)
+            results[idx] = odict
+            self._logger.info(f"Calibrated {raw_images[idx].name} in {time.perf_counter() - t0:.3f} seconds.")
+            slot["pending"] = None
+
+        for idx, raw_path in enumerate(raw_images):
+            slot = slots[idx % ring]
+            finish(slot)                                   # the frame that used this slot before is written out
+            t0 = time.perf_counter()
+            self._check_file_exists(raw_path)
+            lay = fitsio.ImageLayout(raw_path)
+            if tuple(lay.shape) != shape:
+                msg = (f"Error, the shape of the raw image ({tuple(lay.shape)}) does not match that of"
+                       f" the master bias ({shape}).")
+                self._logger.error(msg)
+                raise RuntimeError(msg)
+            hdr = lay.header
+            pedestal = float(hdr["PEDESTAL"]) if "PEDESTAL" in hdr else 0.0
+            exp_ratio = self._find_exptime_ratio(hdr, self._dark_hdr)
+            if slot["consumed"] is not None:
+                slot["consumed"].synchronize()             # the staging buffers' last upload is done
+            if lay.raw_u16:
+                lay.read_rows_raw(0, h, slot["u16_np"])
+                kind, host_t, dev_raw, ped = "u16_fits", slot["u16_t"], slot["raw16"], pedestal
+            else:
+                data, _ = fitsio.read_image(raw_path, 0)
+                np.copyto(slot["f32_np"], data, casting="unsafe")        # reference: astype(float32)
+                if pedestal != 0:
+                    slot["f32_np"] += np.float32(pedestal)
+                kind, host_t, dev_raw, ped = "f32", slot["f32_t"], slot["raw32"], 0.0
+            with torch.cuda.stream(copy_s):
+                if slot["done"] is not None:
+                    copy_s.wait_event(slot["done"])        # the kernel that last read this device buffer is done
+                dev_raw.copy_(host_t, non_blocking=True)
+                up = torch.cuda.Event()
+                up.record(copy_s)
+                slot["consumed"] = up
+            with torch.cuda.stream(comp_s):
+                comp_s.wait_event(up)
+                slot["counts"].zero_()
+                kernels.calibrate_repair(dev_raw, self._bias_dev, self._dark_dev, self._norm_flat_dev, exp_ratio,
+                                         self._dark_still_biased, pedestal=ped, mask=mask_u8, deltapix=int(delta_pix),
+                                         min_valid=self._bpix._min_valid if self._bpix is not None else 4,
+                                         raw_kind=kind, out=slot["out"], out_big_endian=True, counts=slot["counts"])
+                cev = torch.cuda.Event()
+                cev.record(comp_s)
+            with torch.cuda.stream(back_s):
+                back_s.wait_event(cev)
+                slot["out_t"].copy_(slot["out"], non_blocking=True)
+                slot["counts_host"].copy_(slot["counts"], non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(back_s)
+                slot["done"] = done
+            slot["pending"] = (idx, hdr, self._base_odict(), t0)
+        for k in range(ring):
+            finish(slots[(len(raw_images) + k) % ring])
+        return results
+
     # -- file level (reference signature) ------------------------------------
     def calibrate(self, raw_image, cal_image, delta_pix, norm_flat, fixcosmic):
         perf_time_start = time.perf_counter()

@@ -53,6 +53,9 @@ class ApFixBadPixels(ApBase):
                                f"Applied {self._name}", drop_scaling=False, only_bpix=True)
         self._logger.info(f"Wrote bad pixel corrected file to {outdata_file}")
 
+    def _stats_dict(self, npix, nbad, nfixed, deltapix):
+        return _stats_dict_impl(self._min_valid, npix, nbad, nfixed, deltapix)
+
     # -- array level --------------------------------------------------------
     def fix_bad_pixels(self, data, badpixmask, deltapix=1):
         """Return ``(newdata, fixed_stats)``.
@@ -100,16 +103,7 @@ class ApFixBadPixels(ApBase):
         if nnotfix > 0:
             self._logger.warning(f"Could not fix {nnotfix} pixels as they had less"
                                  f" than {self._min_valid} good neighbors when deltapix={deltapix} pixels.")
-        fixed_stats = {
-            "numpix": (npix, "Total number of pixels in image"),
-            "BPIXNBAD": (nbad, "Total number of bad pixels in bad pixel file"),
-            "pctbad": (pctbad, "Percentage of pixel defined bad"),
-            "BPIX_MIN": (self._min_valid, "Minimum number of good neighors needed"),
-            "BPIXDPIX": (deltapix, "Half height/width of collection region (pixels)"),
-            "BPIXNREM": (nnotfix, "Number of bad pixels not corrected"),
-            "BPIXCORR": (nfixed > 0, "True if any bad pixels were corrected"),
-            "BPIXNFIX": (nfixed, "Number of bad pixels corrected"),
-        }
+        fixed_stats = self._stats_dict(npix, nbad, nfixed, deltapix)
         if on_device:
             return out, fixed_stats
         newdata = out.cpu().numpy()
@@ -118,6 +112,20 @@ class ApFixBadPixels(ApBase):
             newdata = np.trunc(newdata).astype(orig_dtype) if not np.issubdtype(orig_dtype, np.floating) \
                 else newdata.astype(orig_dtype)
         return newdata, fixed_stats
+
+
+def _stats_dict_impl(min_valid, npix, nbad, nfixed, deltapix):
+    """The ``fixed_stats`` dictionary of the reference (core/ApFixBadPixels.py:430-443)."""
+    return {
+        "numpix": (npix, "Total number of pixels in image"),
+        "BPIXNBAD": (nbad, "Total number of bad pixels in bad pixel file"),
+        "pctbad": (100.0 * nbad / npix, "Percentage of pixel defined bad"),
+        "BPIX_MIN": (min_valid, "Minimum number of good neighors needed"),
+        "BPIXDPIX": (deltapix, "Half height/width of collection region (pixels)"),
+        "BPIXNREM": (nbad - nfixed, "Number of bad pixels not corrected"),
+        "BPIXCORR": (nfixed > 0, "True if any bad pixels were corrected"),
+        "BPIXNFIX": (nfixed, "Number of bad pixels corrected"),
+    }
 
 
 def _exact_in_f32(a):

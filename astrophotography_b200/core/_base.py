@@ -101,12 +101,9 @@ class ApBase:
                     float(np.nanmin(data)), float(np.nanmax(data)), float(np.nanmedian(data))))
         return data, hdr, pedestal
 
-    def _write_image_like(self, inpdata_file, ext_num, outdata_file, odata, odict,
-                          history, drop_scaling=True, only_bpix=False):
-        """Write ``odata`` with the header of ``inpdata_file`` plus ``odict``."""
-        self._logger.debug(f"FITS header keywords added to output: {odict}")
-        path = self._check_file_exists(inpdata_file)
-        hdr = fitsio.read_header(path, ext_num).copy()
+    def _header_like(self, hdr, odict, history, drop_scaling=True, only_bpix=False):
+        """A copy of ``hdr`` without PEDESTAL (and the scaling keywords), plus ``odict`` and a HISTORY line."""
+        hdr = hdr.copy()
         drop = ["PEDESTAL"] + (["BSCALE", "BZERO"] if drop_scaling else [])
         for kw in drop:
             if kw in hdr:
@@ -117,6 +114,14 @@ class ApBase:
             hdr[kw] = _plain(val)
         tnow = datetime.now().isoformat(timespec="milliseconds")
         hdr["HISTORY"] = f"{history} {__version__} at {tnow}"
+        return hdr
+
+    def _write_image_like(self, inpdata_file, ext_num, outdata_file, odata, odict,
+                          history, drop_scaling=True, only_bpix=False):
+        """Write ``odata`` with the header of ``inpdata_file`` plus ``odict``."""
+        self._logger.debug(f"FITS header keywords added to output: {odict}")
+        path = self._check_file_exists(inpdata_file)
+        hdr = self._header_like(fitsio.read_header(path, ext_num), odict, history, drop_scaling, only_bpix)
         fitsio.write_image(outdata_file, odata, hdr, overwrite=True)
 
 

@@ -280,25 +280,8 @@ def _card(key, val, com=""):
     return _cards_for(key, val, com)[0]
 
 
-def _encode_hdu(data, hdr, primary, extname=None):
+def _encode_header(shape, bitpix, hdr, primary, extname=None, bzero=None):
     cards = []
-    data = None if data is None else np.asarray(data)
-    bzero = None
-    if data is None:
-        bitpix, shape, payload = 8, (), b""
-    else:
-        if data.dtype == np.bool_:
-            data = data.astype(np.uint8)
-        if data.dtype == np.uint16:
-            bitpix, bzero = 16, 32768
-            payload = (data.astype(np.int32) - 32768).astype(">i2").tobytes()
-        else:
-            code = {"u1": 8, "i2": 16, "i4": 32, "i8": 64, "f4": -32, "f8": -64}.get(data.dtype.str[1:])
-            if code is None:
-                raise TypeError(f"cannot write dtype {data.dtype} to FITS")
-            bitpix = code
-            payload = data.astype(data.dtype.newbyteorder(">")).tobytes()
-        shape = data.shape
     cards.append(_card("SIMPLE", True, "conforms to FITS standard") if primary
                  else _card("XTENSION", "IMAGE", "Image extension"))
     cards.append(_card("BITPIX", bitpix, "array data type"))
@@ -328,9 +311,55 @@ def _encode_hdu(data, hdr, primary, extname=None):
                 cards.append(("HISTORY " + text[i:i + 72]).ljust(80))
     cards.append("END".ljust(80))
     head = "".join(cards).encode("ascii", "replace")
-    head += b" " * (-len(head) % BLOCK)
+    return head + b" " * (-len(head) % BLOCK)
+
+
+def _encode_hdu(data, hdr, primary, extname=None):
+    data = None if data is None else np.asarray(data)
+    bzero = None
+    if data is None:
+        bitpix, shape, payload = 8, (), b""
+    else:
+        if data.dtype == np.bool_:
+            data = data.astype(np.uint8)
+        if data.dtype == np.uint16:
+            bitpix, bzero = 16, 32768
+            payload = (data.astype(np.int32) - 32768).astype(">i2").tobytes()
+        else:
+            code = {"u1": 8, "i2": 16, "i4": 32, "i8": 64, "f4": -32, "f8": -64}.get(data.dtype.str[1:])
+            if code is None:
+                raise TypeError(f"cannot write dtype {data.dtype} to FITS")
+            bitpix = code
+            payload = data.astype(data.dtype.newbyteorder(">")).tobytes()
+        shape = data.shape
     payload += b"\0" * (-len(payload) % BLOCK)
-    return head + payload
+    return _encode_header(shape, bitpix, hdr, primary, extname, bzero) + payload
+
+
+def write_data_unit(path, payload, bitpix, shape, header=None, overwrite=True):
+    """Write a primary image HDU whose data unit ``payload`` (a bytes-like object) is ALREADY in FITS byte
+    order -- e.g. the big-endian float32 plane a GPU kernel produced: the header plus one ``write`` of the
+    page-locked buffer, no host-side byte swap.  ``header``: the stand-in ``Header`` or an astropy header."""
+    path = str(path)
+    if os.path.exists(path) and not overwrite:
+        raise OSError(f"{path} exists")
+    buf = memoryview(payload).cast("B")
+    want = abs(int(bitpix)) // 8 * int(np.prod(shape))
+    if buf.nbytes != want:
+        raise ValueError(f"write_data_unit: {buf.nbytes} bytes for a {shape} BITPIX={bitpix} image")
+    hdr = header
+    if hdr is not None and not isinstance(hdr, Header):     # an astropy header: cards through the stand-in
+        h2 = Header()
+        for key in hdr.keys():
+            if key and key not in ("HISTORY", "COMMENT"):
+                h2[key] = (hdr[key], hdr.comments[key])
+        for line in header_history(hdr):
+            h2["HISTORY"] = line
+        hdr = h2
+    with open(path, "wb") as f:
+        f.write(_encode_header(tuple(shape), int(bitpix), hdr, True))
+        f.write(buf)
+        f.write(b"\0" * (-buf.nbytes % BLOCK))
 
 
 # ---------------------------------------------------------------------------

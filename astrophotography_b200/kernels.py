@@ -192,6 +192,48 @@ def calibrate(raw, bias, dark, normflat=None, exp_ratio=1.0, dark_still_biased=F
     return out
 
 
+RAW_KINDS = {"f32": 0, "u16": 1, "u16_fits": 2}       # include/apgpu.h: APGPU_RAW_*
+
+
+def calibrate_repair(raw, bias, dark, normflat=None, exp_ratio=1.0, dark_still_biased=False, pedestal=None,
+                     mask=None, deltapix=2, min_valid=4, raw_kind=None, out=None, out_big_endian=False, counts=None):
+    """Calibration and bad-pixel repair of one frame in ONE launch (``apgpu_calibrate_repair``): what
+    ``calibrate`` followed by ``fix_badpix`` gives, bit for bit, without the intermediate image.
+
+    ``raw``: float32, uint16, or int16/uint16 holding the raw FITS data unit (``raw_kind="u16_fits"``).
+    ``mask``: uint8 CUDA image (non-zero = bad) or None.  Returns ``(out, counts)``; ``out_big_endian``
+    writes the float32 result byte-swapped, ready to be the data unit of a BITPIX=-32 FITS file."""
+    torch = _native.require_cuda()
+    lib = _native.load()
+    _check_image(torch, raw, "raw")
+    _check_image(torch, bias, "bias", torch.float32)
+    _check_image(torch, dark, "dark", torch.float32)
+    if normflat is not None:
+        _check_image(torch, normflat, "normflat", torch.float32)
+    if mask is not None:
+        _check_image(torch, mask, "mask", torch.uint8)
+    for name, t in (("bias", bias), ("dark", dark), ("normflat", normflat), ("mask", mask)):
+        if t is not None and tuple(t.shape) != tuple(raw.shape):
+            raise RuntimeError(f"calibrate_repair: {name} shape {tuple(t.shape)} != raw shape {tuple(raw.shape)}")
+    if raw_kind is None:
+        raw_kind = "f32" if raw.dtype == torch.float32 else "u16"
+    if raw_kind not in RAW_KINDS or (raw_kind == "f32") != (raw.dtype == torch.float32) or \
+            (raw_kind != "f32" and raw.dtype not in (torch.uint16, torch.int16)):
+        raise RuntimeError(f"calibrate_repair: raw dtype {raw.dtype} does not fit raw_kind {raw_kind}")
+    h, w = raw.shape
+    if out is None:
+        out = torch.empty((h, w), dtype=torch.float32, device=raw.device)
+    if mask is not None and counts is None:
+        counts = torch.zeros(2, dtype=torch.int64, device=raw.device)
+    has_ped = pedestal is not None and float(pedestal) != 0.0
+    st = lib.apgpu_calibrate_repair(_ptr(raw), RAW_KINDS[raw_kind], float(pedestal or 0.0), int(has_ped),
+                                    _ptr(bias), _ptr(dark), _ptr(normflat), float(exp_ratio),
+                                    int(bool(dark_still_biased)), _ptr(mask), int(h), int(w), int(deltapix),
+                                    int(min_valid), _ptr(out), int(bool(out_big_endian)), _ptr(counts), _stream(torch))
+    _native.check(st, "apgpu_calibrate_repair")
+    return out, counts
+
+
 _MASK_DTYPES = None
 
 

@@ -375,6 +375,13 @@ def run_gpu(args, shape):
         mask = torch.from_numpy(synth.badpix_mask((h, w), auto_fraction=1e-3)).to(device)
         add_variant("fix_badpix_dp2", lambda: kernels.fix_badpix(cal, mask, 2), mpix, 9 * h * w, steps=5, unit="Mpix/s")
         add_variant("flat_norm_nanmean", lambda: kernels.flat_norm(flat), mpix, 4 * h * w, steps=5, unit="Mpix/s")
+        # the batch driver's launch: calibrate + repair fused (no intermediate image), FITS byte order out
+        add_variant("calibrate_repair_fused_u16_dp2", lambda: kernels.calibrate_repair(raw, bias, dark, nflat, 1.0 / 3.0, True,
+                                                                                      mask=mask, deltapix=2, out=cal, out_big_endian=True),
+                    mpix, 19 * h * w, steps=5, unit="Mpix/s")
+        add_variant("calibrate_then_repair_two_launches_u16_dp2",
+                    lambda: kernels.fix_badpix(kernels.calibrate(raw, bias, dark, nflat, 1.0 / 3.0, True, out=cal), mask, 2),
+                    mpix, 27 * h * w, steps=5, unit="Mpix/s")
         del raw, flat, nflat, cal, mask
 
     # ---- end to end through the host-buffer API (pinned host frames) ----

@@ -189,6 +189,25 @@ int apgpu_fix_badpix_f32(const float* data, const void* mask, int mask_dtype,
                          float* out, int64_t* counts, apgpu_stream_t stream);
 
 /* ------------------------------------------------------------------------
+ * Fused calibration + bad-pixel repair of one science frame (the batch driver's per-frame launch):
+ * ApCalibrate.calibrate, core/ApCalibrate.py:439-479 -- the arithmetic of apgpu_calibrate_* followed by
+ * apgpu_fix_badpix_f32 on its result, bit for bit, without the intermediate image (a bad pixel's donors are
+ * the calibrated values of its neighbours, recomputed on the fly).
+ *
+ * raw, raw_kind   H x W frame: float32, host-order uint16, or the data unit of a BITPIX=16 / BZERO=32768
+ *                 FITS image as stored on disk (big-endian int16 + 32768)
+ * mask            uint8, non-zero = bad; NULL = calibrate only (counts may then be NULL too)
+ * out_big_endian  non-zero: write big-endian float32, i.e. the data unit of a BITPIX=-32 FITS image
+ * counts          device int64[2]: += {bad pixels, repaired} (caller zeroes it)
+ * ---------------------------------------------------------------------- */
+enum { APGPU_RAW_F32 = 0, APGPU_RAW_U16 = 1, APGPU_RAW_U16_FITS = 2 };
+int apgpu_calibrate_repair(const void* raw, int raw_kind, float pedestal, int has_pedestal,
+                           const float* bias, const float* dark, const float* normflat,
+                           float exp_ratio, int dark_still_biased,
+                           const uint8_t* mask, int64_t H, int64_t W, int deltapix, int min_valid,
+                           float* out, int out_big_endian, int64_t* counts, apgpu_stream_t stream);
+
+/* ------------------------------------------------------------------------
  * Whole-image sigma-clipped statistics and threshold mask: the arithmetic of the
  * mask producer ApFindBadPixels._generate_sigmaclip_mask,
  * core/ApFindBadPixels.py:191-209.

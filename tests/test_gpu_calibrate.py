@@ -114,3 +114,51 @@ def test_calibrate_errors(cuda):
         kernels.calibrate(a.cpu(), a, a)
     with pytest.raises(RuntimeError):
         kernels.calibrate(a.to(torch.float64), a, a)
+
+
+# ---------------------------------------------------------------- fused calibrate + repair (batch driver's launch)
+@pytest.mark.parametrize("raw_kind", ["f32", "u16", "u16_fits"])
+@pytest.mark.parametrize("dp", [1, 2, 3])
+@pytest.mark.parametrize("shape", [(64, 96), (37, 53)])           # vector path / scalar path (W % 4 != 0)
+def test_fused_calibrate_repair_equals_two_launches(cuda, raw_kind, dp, shape):
+    """apgpu_calibrate_repair == apgpu_calibrate_* followed by apgpu_fix_badpix_f32, bit for bit (float32 raw,
+    host-order uint16 raw with PEDESTAL, and the big-endian BZERO=32768 FITS data unit), for every flat / bias
+    mode; the big-endian output option is the byte-swapped plane."""
+    torch = cuda
+    from astrophotography_b200 import kernels, synth
+    rng = np.random.default_rng(dp * 100 + shape[0])
+    raw16 = synth.science_frame(shape, seed=3, as_uint16=True, nstars=4)
+    raw16[0, :4] = [0, 65535, 32767, 32768]
+    bias = rng.normal(1000, 5, shape).astype(np.float32)
+    dark = rng.normal(1040, 6, shape).astype(np.float32)
+    flat = synth.flat_frame(shape, seed=7)
+    mask = synth.badpix_mask(shape, seed=13, auto_fraction=2e-2)
+    mask[5:9, 10:14] = 1                                          # an unfixable block interior at dp=1
+    nf, _ = kernels.flat_normalise(torch.from_numpy(flat).cuda())
+    b_d, d_d, m_d = torch.from_numpy(bias).cuda(), torch.from_numpy(dark).cuda(), torch.from_numpy(mask).cuda()
+    if raw_kind == "f32":
+        raw_d, raw_ref, ped = torch.from_numpy(raw16.astype(np.float32) + np.float32(-100.0)).cuda(), None, None
+    elif raw_kind == "u16":
+        raw_d, ped = torch.from_numpy(raw16.view(np.int16)).cuda().view(torch.uint16), -100.0
+    else:
+        be = (raw16.astype(np.int32) - 32768).astype(">i2")
+        raw_d, ped = torch.from_numpy(np.ascontiguousarray(be).view(np.int16).copy()).cuda(), -100.0
+    for flat_on in (True, False):
+        for biased in (True, False):
+            nfl = nf if flat_on else None
+            if raw_kind == "f32":
+                cal = kernels.calibrate(raw_d, b_d, d_d, nfl, 1.0 / 3.0, biased)
+            else:
+                u16_d = torch.from_numpy(raw16.view(np.int16)).cuda().view(torch.uint16)
+                cal = kernels.calibrate(u16_d, b_d, d_d, nfl, 1.0 / 3.0, biased, pedestal=ped)
+            exp, ecounts = kernels.fix_badpix(cal, m_d, dp)
+            got, counts = kernels.calibrate_repair(raw_d, b_d, d_d, nfl, 1.0 / 3.0, biased, pedestal=ped, mask=m_d,
+                                                   deltapix=dp, raw_kind=raw_kind)
+            assert bits_equal(got.cpu().numpy(), exp.cpu().numpy()), (raw_kind, dp, flat_on, biased)
+            assert counts.tolist() == ecounts.tolist() and counts[0].item() == int((mask != 0).sum())
+            nomask, _ = kernels.calibrate_repair(raw_d, b_d, d_d, nfl, 1.0 / 3.0, biased, pedestal=ped, raw_kind=raw_kind)
+            assert bits_equal(nomask.cpu().numpy(), cal.cpu().numpy())
+    be_out, _ = kernels.calibrate_repair(raw_d, b_d, d_d, nf, 1.0 / 3.0, True, pedestal=ped, mask=m_d, deltapix=dp,
+                                         raw_kind=raw_kind, out_big_endian=True)
+    ref = kernels.calibrate_repair(raw_d, b_d, d_d, nf, 1.0 / 3.0, True, pedestal=ped, mask=m_d, deltapix=dp, raw_kind=raw_kind)[0]
+    assert np.array_equal(be_out.cpu().numpy().view(">f4").astype("=f4").view(np.uint32), ref.cpu().numpy().view(np.uint32))

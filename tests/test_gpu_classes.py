@@ -252,6 +252,54 @@ def test_make_master_overlaps_file_reads_with_uploads(cuda, tmp_path):
     assert t_files <= 1.3 * (t_read + t_comb)
 
 
+def test_calibrate_many_equals_per_frame_calibrate(cuda, tmp_path):
+    """The batch driver (masters resident, three streams, fused calibrate + repair, FITS byte order produced on
+    the GPU) writes the same pixels and keywords as one ApCalibrate.calibrate call per frame; the ap_calibrate_all
+    CLI skips existing outputs like calibrate_all.sh."""
+    import astrophotography_b200 as ap
+    from astrophotography_b200 import fitsio, synth
+    from astrophotography_b200.scripts import ap_calibrate_all
+    shape = (48, 72)
+    rng = np.random.default_rng(5)
+    bias = _fits(tmp_path / "mbias.fits", rng.normal(1000, 5, shape).astype(np.float32))
+    dark = _fits(tmp_path / "mdark.fits", rng.normal(1040, 6, shape).astype(np.float32), EXPTIME=900.0)
+    flat = _fits(tmp_path / "mflat.fits", synth.flat_frame(shape))
+    mask = _fits(tmp_path / "mask.fits", synth.badpix_mask(shape, auto_fraction=1e-2))
+    rawdir = tmp_path / "raw"
+    rawdir.mkdir()
+    raws = []
+    for k in range(7):
+        fr = synth.science_frame(shape, seed=20 + k, as_uint16=(k != 3), nstars=3)
+        cards = {"EXPTIME": 300.0 + 10 * k, "OBJECT": f"T{k}"}
+        if k % 2:
+            cards["PEDESTAL"] = -100
+        raws.append(_fits(rawdir / f"raw{k}.fits", fr, **cards))
+    cal = ap.ApCalibrate(bias, dark, flat, mask, "ERROR", True)
+    outs = [str(tmp_path / f"many{k}.fits") for k in range(7)]
+    odicts = cal.calibrate_many(raws, outs, 2)
+    assert len(odicts) == 7 and all(o["BIASCORR"][0] for o in odicts)
+    for k in range(7):
+        one = str(tmp_path / f"one{k}.fits")
+        cal.calibrate(raws[k], one, 2, None, False)
+        a, ha = fitsio.read_image(outs[k], 0)
+        b, hb = fitsio.read_image(one, 0)
+        assert a.dtype == np.float32 and bits_equal(a, b), k
+        for kw in ("BIASCORR", "BIASFILE", "DARKCORR", "DARKFILE", "BUNIT", "FLATCORR", "FLATFILE", "BPIXFILE", "BPIXNBAD",
+                   "BPIXNFIX", "BPIXNREM", "BPIXDPIX", "BPIX_MIN", "BPIXCORR", "OBJECT", "EXPTIME"):
+            assert ha[kw] == hb[kw], (k, kw)
+        assert "PEDESTAL" not in ha and "BZERO" not in ha
+        assert any("Processed by ApCalibrate" in ln for ln in fitsio.header_history(ha))
+    outdir = tmp_path / "out"
+    argv = [str(rawdir), bias, dark, str(outdir), "--master_flat", flat, "--master_badpix", mask, "--dark_still_biased", "-l", "ERROR"]
+    assert ap_calibrate_all.main(argv) == 0
+    for k in range(7):
+        a, _ = fitsio.read_image(outdir / f"cal-raw{k}.fits", 0)
+        b, _ = fitsio.read_image(outs[k], 0)
+        assert bits_equal(a, b)
+    stamp = os.path.getmtime(outdir / "cal-raw0.fits")
+    assert ap_calibrate_all.main(argv) == 0 and os.path.getmtime(outdir / "cal-raw0.fits") == stamp      # skipped
+
+
 def test_master_keeps_pedestal_and_apcalibrate_removes_it(cuda, tmp_path):
     """MaximDL-style frames carry PEDESTAL=-100.  Like ccdproc.combine the master keeps the keyword (the
     frames are combined as stored) and ApCalibrate._read_fits removes the pedestal from the master bias /
