@@ -5,14 +5,13 @@
 // the good pixels of the ORIGINAL data inside the (2*dp+1)^2 window clipped to
 // the image (:383-394), provided at least min_valid=4 good ones exist (:397).
 //
-// Here: one dense pass, HBM-bound (4 B read + mask + 4 B write per pixel).  Each
-// thread copies four adjacent pixels with 128-bit accesses.  When a warp meets
-// bad pixels it repairs them one after the other COOPERATIVELY: the 32 lanes
-// fetch the <= 24 donors of the 5x5 window in parallel (neighbour rows are L1/L2
-// hits: the warp has just streamed them), sort them with a bitonic network of
-// warp shuffles (+inf for non-donors) and read back the middle order
-// statistics.  Donors come from the input image only, so every pixel is
-// independent: no halo exchange, no second pass.
+// Here: a dense copy kernel at copy bandwidth (4 B read + 4 B write per pixel, 128-bit
+// streaming accesses) followed by a persistent mask-scan kernel (1 B per pixel, eight
+// 16-byte loads in flight per thread) in which only the warps that meet bad pixels work:
+// they repair them one after the other COOPERATIVELY -- the 32 lanes fetch the <= 24 donors
+// of the 5x5 window in parallel, sort them with a bitonic network of warp shuffles (+inf
+// for non-donors) and read back the middle order statistics (badpix_common.cuh).  Donors
+// come from the input image only, so every pixel is independent: no halo exchange.
 //
 // np.median semantics kept bit-exact: odd count -> middle value; even count ->
 // float32(a + b) / 2 (numpy takes the mean of the two middle float32 values in
@@ -22,98 +21,52 @@
 namespace {
 using namespace apgpu_badpix;
 
-// grid.x covers the 4-pixel groups of one row (whole warps), grid.y the rows of the band.
-template <int DP, typename MaskT>
+// dense pass: the produced rows of the band at copy bandwidth (128-bit streaming accesses, four independent
+// vectors in flight per thread)
+constexpr int CP_UNROLL = 4;
+
 __global__ void __launch_bounds__(BP_THREADS)
-fix_badpix_kernel(const float* __restrict__ data, const MaskT* __restrict__ mask,
-                  int64_t H, int64_t W, int64_t band_row0, int64_t row0, int64_t nrows,
-                  int dp, int min_valid, float* __restrict__ out,
-                  unsigned long long* __restrict__ counts, bool vec_ok) {
-    const int64_t groups_per_row = (W + 3) / 4;
-    const int64_t g = (int64_t)blockIdx.x * BP_THREADS + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    // whole warps stay in the loop together (a warp whose first group is past the row leaves as one)
-    const bool warp_active = (g - lane) < groups_per_row;
-    unsigned nbad = 0, nfix = 0;
-    for (int64_t rel = blockIdx.y; warp_active && rel < nrows; rel += gridDim.y) {
-        const int64_t r = row0 + rel;
-        const int64_t c0 = g * 4;
-        const int64_t in_base = (r - band_row0) * W + c0;
-        const int64_t out_base = rel * W + c0;
-        float px[4] = {0.f, 0.f, 0.f, 0.f};
-        bool bad[4] = {false, false, false, false};
-        const int nvalid = g < groups_per_row ? (int)((W - c0) < 4 ? (W - c0) : 4) : 0;
-        if (vec_ok && nvalid == 4) {
-            const float4 d = ld_stream(reinterpret_cast<const float4*>(data + in_base));
-            px[0] = d.x; px[1] = d.y; px[2] = d.z; px[3] = d.w;
-            if (sizeof(MaskT) == 1) {
-                const uchar4 m4 = __ldcs(reinterpret_cast<const uchar4*>(mask + in_base));
-                bad[0] = m4.x != 0; bad[1] = m4.y != 0; bad[2] = m4.z != 0; bad[3] = m4.w != 0;
-            } else {
+badpix_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t nvec) {
+    const int64_t base = (int64_t)blockIdx.x * (BP_THREADS * CP_UNROLL) + threadIdx.x;
+    float4 v[CP_UNROLL];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) bad[k] = mask_bad(mask, in_base + k);
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (k < nvalid) { px[k] = data[in_base + k]; bad[k] = mask_bad(mask, in_base + k); }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (DP == 1 || DP == 2) {
-                unsigned todo = __ballot_sync(0xffffffffu, bad[k]);
-                nbad += bad[k] ? 1u : 0u;
-                while (todo) {
-                    const int src = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    const int64_t cc = __shfl_sync(0xffffffffu, c0, src) + k;
-                    float res = 0.f;
-                    const bool ok = repair_warp<(DP == 1 || DP == 2) ? DP : 1, MaskT>(
-                        PlainImage{data}, mask, H, W, band_row0, r, cc, min_valid, res);
-                    if (ok && lane == src) { px[k] = res; ++nfix; }
-                }
-            } else if (bad[k]) {
-                ++nbad;
-                float res;
-                if (repair_any<MaskT>(PlainImage{data}, mask, H, W, band_row0, r, c0 + k, dp, min_valid, res)) { px[k] = res; ++nfix; }
-            }
-        }
-        if (vec_ok && nvalid == 4) {
-            st_stream(reinterpret_cast<float4*>(out + out_base), make_float4(px[0], px[1], px[2], px[3]));
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) if (k < nvalid) out[out_base + k] = px[k];
-        }
+    for (int u = 0; u < CP_UNROLL; ++u) {
+        const int64_t i = base + (int64_t)u * BP_THREADS;
+        if (i < nvec) v[u] = ld_stream(reinterpret_cast<const float4*>(src) + i);
     }
-    // warp-aggregated counters
-    for (int off = 16; off > 0; off >>= 1) {
-        nbad += __shfl_down_sync(0xffffffffu, nbad, off);
-        nfix += __shfl_down_sync(0xffffffffu, nfix, off);
+#pragma unroll
+    for (int u = 0; u < CP_UNROLL; ++u) {
+        const int64_t i = base + (int64_t)u * BP_THREADS;
+        if (i < nvec) st_stream(reinterpret_cast<float4*>(dst) + i, v[u]);
     }
-    if (lane == 0 && nbad) {
-        atomicAdd(&counts[0], (unsigned long long)nbad);
-        if (nfix) atomicAdd(&counts[1], (unsigned long long)nfix);
-    }
+}
+
+__global__ void __launch_bounds__(BP_THREADS)
+badpix_copy_scalar_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t i0, int64_t n) {
+    const int64_t i = i0 + (int64_t)blockIdx.x * BP_THREADS + threadIdx.x;
+    if (i < n) dst[i] = src[i];
 }
 
 template <typename MaskT>
 int launch_bp(const float* data, const MaskT* mask, int64_t H, int64_t W, int64_t band_row0,
               int64_t row0, int64_t nrows, int dp, int min_valid, float* out, int64_t* counts,
               cudaStream_t st) {
-    int64_t groups = (W + 3) / 4;
-    dim3 grid((unsigned)((groups + BP_THREADS - 1) / BP_THREADS),
-              (unsigned)(nrows < 65535 ? nrows : 65535));
-    bool vec_ok = (W % 4 == 0) && apgpu_aligned(data, 16) && apgpu_aligned(out, 16) && apgpu_aligned(mask, 4);
-    unsigned long long* c = reinterpret_cast<unsigned long long*>(counts);
-    if (dp == 1)
-        fix_badpix_kernel<1, MaskT><<<grid, BP_THREADS, 0, st>>>(data, mask, H, W, band_row0, row0, nrows, dp, min_valid, out, c, vec_ok);
-    else if (dp == 2)
-        fix_badpix_kernel<2, MaskT><<<grid, BP_THREADS, 0, st>>>(data, mask, H, W, band_row0, row0, nrows, dp, min_valid, out, c, vec_ok);
-    else
-        fix_badpix_kernel<0, MaskT><<<grid, BP_THREADS, 0, st>>>(data, mask, H, W, band_row0, row0, nrows, dp, min_valid, out, c, vec_ok);
-    APGPU_LAUNCH_CHECK("fix_badpix_kernel");
-    return APGPU_OK;
+    // 1. every produced pixel, unrepaired; 2. the mask scan overwrites the repaired ones (donors come from `data`)
+    const float* first = data + (row0 - band_row0) * W;
+    const int64_t n = nrows * W;
+    const int64_t nvec = (apgpu_aligned(first, 16) && apgpu_aligned(out, 16)) ? n / 4 : 0;
+    if (nvec > 0) {
+        const int64_t per_block = BP_THREADS * CP_UNROLL;
+        badpix_copy_kernel<<<(unsigned)((nvec + per_block - 1) / per_block), BP_THREADS, 0, st>>>(first, out, nvec);
+        APGPU_LAUNCH_CHECK("badpix_copy_kernel");
+    }
+    if (nvec * 4 < n) {
+        const int64_t rem = n - nvec * 4;
+        badpix_copy_scalar_kernel<<<(unsigned)((rem + BP_THREADS - 1) / BP_THREADS), BP_THREADS, 0, st>>>(first, out, nvec * 4, n);
+        APGPU_LAUNCH_CHECK("badpix_copy_scalar_kernel");
+    }
+    return launch_repair_scan<MaskT>(PlainImage{data}, mask, H, W, band_row0, row0, nrows, dp, min_valid, out, false,
+                                     counts, st);
 }
 
 }  // namespace

@@ -1,12 +1,12 @@
-// Fused science-frame calibration + bad-pixel repair (sm_100a): one launch per frame for the batch driver.
+// Fused science-frame calibration + bad-pixel repair (sm_100a): one call per frame for the batch driver.
 //
 // Reference: ApCalibrate.calibrate, AstroPhotography/core/ApCalibrate.py:439-479 -- the numpy calibration
 // arithmetic (:439-474) immediately followed by ApFixBadPixels.fix_bad_pixels on its result (:478-479).  Run as
 // two kernels that intermediate image costs 8 more bytes per pixel of HBM traffic (4 written, 4 read again); here
-// every pixel is calibrated in registers and written once, and a bad pixel's donors -- the CALIBRATED values of
-// its good neighbours -- are recomputed from raw / bias / dark / flat on the fly (<= 24 neighbours of ~1 % of the
-// pixels: the rows are L1/L2 hits, the warp has just streamed them).  The arithmetic is the same explicitly
-// rounded float32 sequence as calibrate.cu and the same warp-cooperative median as badpix.cu (badpix_common.cuh),
+// a streaming kernel calibrates every pixel at copy bandwidth and a persistent mask scan then overwrites the
+// repaired ones (badpix_common.cuh); a bad pixel's donors -- the CALIBRATED values of its good neighbours -- are recomputed from raw / bias / dark /
+// flat on the fly (<= 24 neighbours of ~1 % of the pixels), so the intermediate image is never read back.  The
+// arithmetic is the same explicitly rounded float32 sequence as calibrate.cu and the same warp-cooperative median as badpix.cu (badpix_common.cuh),
 // so the output equals apgpu_calibrate_* followed by apgpu_fix_badpix_f32 bit for bit.
 //
 // The raw frame may be float32, host-order uint16, or the data unit of a BITPIX=16 / BZERO=32768 FITS file as it
@@ -56,102 +56,92 @@ struct CalibratedImage {
     __device__ __forceinline__ float at(int64_t i) const {
         return cal1(p, decode_raw(p, i), p.bias[i], p.dark[i], p.nflat ? p.nflat[i] : 1.f);
     }
+    // four consecutive pixels starting at a multiple of 4 (128-bit streaming loads)
+    __device__ __forceinline__ float4 vec4(int64_t i) const {
+        float rv[4];
+        if (p.raw_kind == APGPU_RAW_F32) {
+            const float4 v = ld_stream(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.raw) + i));
+            rv[0] = v.x; rv[1] = v.y; rv[2] = v.z; rv[3] = v.w;
+        } else {
+            const ushort4 w = __ldcs(reinterpret_cast<const ushort4*>(reinterpret_cast<const uint16_t*>(p.raw) + i));
+            uint32_t w4[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (p.raw_kind == APGPU_RAW_U16_FITS) w4[k] = (__byte_perm(w4[k], 0u, 0x4401) ^ 0x8000u) & 0xffffu;
+                rv[k] = (float)w4[k];
+            }
+        }
+        if (p.has_ped) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) rv[k] = __fadd_rn(rv[k], p.ped);
+        }
+        const float4 b = ld_stream(reinterpret_cast<const float4*>(p.bias + i));
+        const float4 d = ld_stream(reinterpret_cast<const float4*>(p.dark + i));
+        const float4 f = p.nflat ? ld_stream(reinterpret_cast<const float4*>(p.nflat + i)) : make_float4(1.f, 1.f, 1.f, 1.f);
+        return make_float4(cal1(p, rv[0], b.x, d.x, f.x), cal1(p, rv[1], b.y, d.y, f.y),
+                           cal1(p, rv[2], b.z, d.z, f.z), cal1(p, rv[3], b.w, d.w, f.w));
+    }
 };
 
 __device__ __forceinline__ float to_big_endian(float v) {
     return __uint_as_float(__byte_perm(__float_as_uint(v), 0u, 0x0123));
 }
 
-template <int DP>
+// dense pass: the calibration arithmetic at copy bandwidth -- 128-bit streaming accesses, two independent
+// vectors in flight per thread (like calibrate_vec4_kernel), raw decode and output byte order chosen at run time
+constexpr int CR_UNROLL = 2;
+
 __global__ void __launch_bounds__(BP_THREADS)
-calibrate_repair_kernel(const __grid_constant__ CalParams p, const uint8_t* __restrict__ mask,
-                        int64_t H, int64_t W, int dp, int min_valid, float* __restrict__ out, int out_big_endian,
-                        unsigned long long* __restrict__ counts, bool vec_ok) {
-    const CalibratedImage img{p};
-    const int64_t groups_per_row = (W + 3) / 4;
-    const int64_t g = (int64_t)blockIdx.x * BP_THREADS + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    const bool warp_active = (g - lane) < groups_per_row;          // whole warps stay in the loop together
-    unsigned nbad = 0, nfix = 0;
-    for (int64_t r = blockIdx.y; warp_active && r < H; r += gridDim.y) {
-        const int64_t c0 = g * 4;
-        const int64_t base = r * W + c0;
-        float px[4] = {0.f, 0.f, 0.f, 0.f};
-        bool bad[4] = {false, false, false, false};
-        const int nvalid = g < groups_per_row ? (int)((W - c0) < 4 ? (W - c0) : 4) : 0;
-        if (vec_ok && nvalid == 4) {
-            float rv[4];
+calibrate_stream_kernel(const __grid_constant__ CalParams p, float* __restrict__ out, int out_big_endian, int64_t nvec) {
+    const int64_t base = (int64_t)blockIdx.x * (BP_THREADS * CR_UNROLL) + threadIdx.x;
+    float rv[CR_UNROLL][4];
+    float4 b[CR_UNROLL], d[CR_UNROLL], f[CR_UNROLL];
+#pragma unroll
+    for (int u = 0; u < CR_UNROLL; ++u) {
+        const int64_t i = base + (int64_t)u * BP_THREADS;
+        if (i < nvec) {
             if (p.raw_kind == APGPU_RAW_F32) {
-                const float4 v = ld_stream(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.raw) + base));
-                rv[0] = v.x; rv[1] = v.y; rv[2] = v.z; rv[3] = v.w;
+                const float4 v = ld_stream(reinterpret_cast<const float4*>(p.raw) + i);
+                rv[u][0] = v.x; rv[u][1] = v.y; rv[u][2] = v.z; rv[u][3] = v.w;
             } else {
-                const ushort4 u = __ldcs(reinterpret_cast<const ushort4*>(reinterpret_cast<const uint16_t*>(p.raw) + base));
-                uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+                const ushort4 w = __ldcs(reinterpret_cast<const ushort4*>(p.raw) + i);
+                uint32_t w4[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     if (p.raw_kind == APGPU_RAW_U16_FITS) w4[k] = (__byte_perm(w4[k], 0u, 0x4401) ^ 0x8000u) & 0xffffu;
-                    rv[k] = (float)w4[k];
+                    rv[u][k] = (float)w4[k];
                 }
             }
+            b[u] = ld_stream(reinterpret_cast<const float4*>(p.bias) + i);
+            d[u] = ld_stream(reinterpret_cast<const float4*>(p.dark) + i);
+            f[u] = p.nflat ? ld_stream(reinterpret_cast<const float4*>(p.nflat) + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < CR_UNROLL; ++u) {
+        const int64_t i = base + (int64_t)u * BP_THREADS;
+        if (i < nvec) {
             if (p.has_ped) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) rv[k] = __fadd_rn(rv[k], p.ped);
+                for (int k = 0; k < 4; ++k) rv[u][k] = __fadd_rn(rv[u][k], p.ped);
             }
-            const float4 b = ld_stream(reinterpret_cast<const float4*>(p.bias + base));
-            const float4 d = ld_stream(reinterpret_cast<const float4*>(p.dark + base));
-            float4 f = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (p.nflat) f = ld_stream(reinterpret_cast<const float4*>(p.nflat + base));
-            px[0] = cal1(p, rv[0], b.x, d.x, f.x); px[1] = cal1(p, rv[1], b.y, d.y, f.y);
-            px[2] = cal1(p, rv[2], b.z, d.z, f.z); px[3] = cal1(p, rv[3], b.w, d.w, f.w);
-            if (mask) {
-                const uchar4 m4 = __ldcs(reinterpret_cast<const uchar4*>(mask + base));
-                bad[0] = m4.x != 0; bad[1] = m4.y != 0; bad[2] = m4.z != 0; bad[3] = m4.w != 0;
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (k < nvalid) { px[k] = img.at(base + k); bad[k] = mask && mask[base + k] != 0; }
-            }
-        }
-        if (mask) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (DP == 1 || DP == 2) {
-                    unsigned todo = __ballot_sync(0xffffffffu, bad[k]);
-                    nbad += bad[k] ? 1u : 0u;
-                    while (todo) {
-                        const int src = __ffs(todo) - 1;
-                        todo &= todo - 1;
-                        const int64_t cc = __shfl_sync(0xffffffffu, c0, src) + k;
-                        float res = 0.f;
-                        const bool ok = repair_warp<(DP == 1 || DP == 2) ? DP : 1, uint8_t>(img, mask, H, W, 0, r, cc, min_valid, res);
-                        if (ok && lane == src) { px[k] = res; ++nfix; }
-                    }
-                } else if (bad[k]) {
-                    ++nbad;
-                    float res;
-                    if (repair_any<uint8_t>(img, mask, H, W, 0, r, c0 + k, dp, min_valid, res)) { px[k] = res; ++nfix; }
-                }
-            }
-        }
-        if (out_big_endian) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) px[k] = to_big_endian(px[k]);
-        }
-        if (vec_ok && nvalid == 4) {
-            st_stream(reinterpret_cast<float4*>(out + base), make_float4(px[0], px[1], px[2], px[3]));
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) if (k < nvalid) out[base + k] = px[k];
+            float4 o;
+            o.x = cal1(p, rv[u][0], b[u].x, d[u].x, f[u].x); o.y = cal1(p, rv[u][1], b[u].y, d[u].y, f[u].y);
+            o.z = cal1(p, rv[u][2], b[u].z, d[u].z, f[u].z); o.w = cal1(p, rv[u][3], b[u].w, d[u].w, f[u].w);
+            if (out_big_endian) { o.x = to_big_endian(o.x); o.y = to_big_endian(o.y); o.z = to_big_endian(o.z); o.w = to_big_endian(o.w); }
+            st_stream(reinterpret_cast<float4*>(out) + i, o);
         }
     }
-    for (int off = 16; off > 0; off >>= 1) {
-        nbad += __shfl_down_sync(0xffffffffu, nbad, off);
-        nfix += __shfl_down_sync(0xffffffffu, nfix, off);
-    }
-    if (lane == 0 && nbad) {
-        atomicAdd(&counts[0], (unsigned long long)nbad);
-        if (nfix) atomicAdd(&counts[1], (unsigned long long)nfix);
+}
+
+__global__ void __launch_bounds__(BP_THREADS)
+calibrate_stream_scalar_kernel(const __grid_constant__ CalParams p, float* __restrict__ out, int out_big_endian,
+                               int64_t i0, int64_t n) {
+    const CalibratedImage img{p};
+    const int64_t i = i0 + (int64_t)blockIdx.x * BP_THREADS + threadIdx.x;
+    if (i < n) {
+        const float v = img.at(i);
+        out[i] = out_big_endian ? to_big_endian(v) : v;
     }
 }
 
@@ -174,19 +164,27 @@ extern "C" int apgpu_calibrate_repair(const void* raw, int raw_kind, float pedes
     p.raw = raw; p.bias = bias; p.dark = dark; p.nflat = normflat;
     p.ped = pedestal; p.r = exp_ratio; p.raw_kind = raw_kind;
     p.has_ped = has_pedestal != 0; p.biased = dark_still_biased != 0;
-    const int64_t groups = (W + 3) / 4;
-    dim3 grid((unsigned)((groups + BP_THREADS - 1) / BP_THREADS), (unsigned)(H < 65535 ? H : 65535));
-    const size_t raw_align = raw_kind == APGPU_RAW_F32 ? 16 : 8;
-    const bool vec_ok = (W % 4 == 0) && apgpu_aligned(raw, raw_align) && apgpu_aligned(bias, 16) && apgpu_aligned(dark, 16) &&
-                        apgpu_aligned(out, 16) && (!normflat || apgpu_aligned(normflat, 16)) && (!mask || apgpu_aligned(mask, 4));
-    unsigned long long* c = reinterpret_cast<unsigned long long*>(counts);
     cudaStream_t st = (cudaStream_t)stream;
-    if (!mask || deltapix == 1)
-        calibrate_repair_kernel<1><<<grid, BP_THREADS, 0, st>>>(p, mask, H, W, deltapix, min_valid, out, out_big_endian, c, vec_ok);
-    else if (deltapix == 2)
-        calibrate_repair_kernel<2><<<grid, BP_THREADS, 0, st>>>(p, mask, H, W, deltapix, min_valid, out, out_big_endian, c, vec_ok);
-    else
-        calibrate_repair_kernel<0><<<grid, BP_THREADS, 0, st>>>(p, mask, H, W, deltapix, min_valid, out, out_big_endian, c, vec_ok);
-    APGPU_LAUNCH_CHECK("calibrate_repair_kernel");
+    const int64_t npix = H * W;
+    const size_t raw_align = raw_kind == APGPU_RAW_F32 ? 16 : 8;
+    const bool vec_ok = apgpu_aligned(raw, raw_align) && apgpu_aligned(bias, 16) && apgpu_aligned(dark, 16) &&
+                        apgpu_aligned(out, 16) && (!normflat || apgpu_aligned(normflat, 16));
+    // 1. every pixel calibrated, unrepaired, at streaming speed
+    const int64_t nvec = vec_ok ? npix / 4 : 0;
+    if (nvec > 0) {
+        const int64_t per_block = BP_THREADS * CR_UNROLL;
+        calibrate_stream_kernel<<<(unsigned)((nvec + per_block - 1) / per_block), BP_THREADS, 0, st>>>(p, out, out_big_endian, nvec);
+        APGPU_LAUNCH_CHECK("calibrate_stream_kernel");
+    }
+    if (nvec * 4 < npix) {
+        const int64_t rem = npix - nvec * 4;
+        calibrate_stream_scalar_kernel<<<(unsigned)((rem + BP_THREADS - 1) / BP_THREADS), BP_THREADS, 0, st>>>(
+            p, out, out_big_endian, nvec * 4, npix);
+        APGPU_LAUNCH_CHECK("calibrate_stream_scalar_kernel");
+    }
+    // 2. the mask scan overwrites the repaired pixels; their donors are recomputed from the inputs
+    if (mask)
+        return launch_repair_scan<uint8_t>(CalibratedImage{p}, mask, H, W, 0, 0, H, deltapix, min_valid, out,
+                                           out_big_endian != 0, counts, st);
     return APGPU_OK;
 }
