@@ -45,6 +45,7 @@ SIGNATURES = {
                                         _P, _P, _P]),
     "apgpu_calibrate_repair": (_c.c_int, [_P, _c.c_int, _c.c_float, _c.c_int, _P, _P, _P, _c.c_float, _c.c_int,
                                           _P, _c.c_int64, _c.c_int64, _c.c_int, _c.c_int, _P, _c.c_int, _P, _P]),
+    "apgpu_imarith_f32": (_c.c_int, [_P, _P, _c.c_int, _c.c_double, _c.c_int, _P, _c.c_int64, _P]),
     "apgpu_image_stats_workspace_bytes": (_c.c_size_t, [_c.c_int64]),
     "apgpu_sigma_clipped_stats_f32": (_c.c_int, [_P, _c.c_int64, _c.c_double, _c.c_int, _P,
                                                  _c.c_size_t, _P, _P]),

@@ -61,6 +61,7 @@ SOURCES = ['stack_sorted_med_f32_p3.cu',
            'apgpu_core.cu',
            'calibrate.cu',
            'calibrate_repair.cu',
+           'imarith.cu',
            'badpix.cu',
            'stats.cu']
 NVCC_FLAGS = [

@@ -2,6 +2,7 @@
 from .ApCalibrate import ApCalibrate
 from .ApFindBadPixels import ApFindBadPixels
 from .ApFixBadPixels import ApFixBadPixels
+from .ApImArith import ApImArith
 from .ApMasterCal import ApMasterCal
 
-__all__ = ["ApCalibrate", "ApFindBadPixels", "ApFixBadPixels", "ApMasterCal"]
+__all__ = ["ApCalibrate", "ApFindBadPixels", "ApFixBadPixels", "ApImArith", "ApMasterCal"]

@@ -234,6 +234,32 @@ def calibrate_repair(raw, bias, dark, normflat=None, exp_ratio=1.0, dark_still_b
     return out, counts
 
 
+IMARITH_OPS = {"ADD": 0, "SUB": 1, "MUL": 2, "DIV": 3}
+
+
+def imarith(a, op, b, out=None):
+    """``np.<op>(a, b, out=float32)`` for a float32 CUDA image ``a`` and ``b`` a Python number, a float32 or a
+    float64 CUDA image (core/ApImArith.py:321-333)."""
+    torch = _native.require_cuda()
+    lib = _native.load()
+    _check_image(torch, a, "a", torch.float32)
+    if op not in IMARITH_OPS:
+        raise RuntimeError(f"imarith: bad operation {op}")
+    if out is None:
+        out = torch.empty_like(a)
+    if isinstance(b, torch.Tensor):
+        _check_image(torch, b, "b")
+        if tuple(b.shape) != tuple(a.shape) or b.dtype not in (torch.float32, torch.float64):
+            raise RuntimeError(f"imarith: second image {tuple(b.shape)} {b.dtype} does not fit {tuple(a.shape)} float32")
+        st = lib.apgpu_imarith_f32(_ptr(a), _ptr(b), 1 if b.dtype == torch.float32 else 2, 0.0, IMARITH_OPS[op],
+                                   _ptr(out), a.numel(), _stream(torch))
+    else:
+        st = lib.apgpu_imarith_f32(_ptr(a), ctypes.c_void_p(0), 0, float(b), IMARITH_OPS[op], _ptr(out), a.numel(),
+                                   _stream(torch))
+    _native.check(st, "apgpu_imarith_f32")
+    return out
+
+
 _MASK_DTYPES = None
 
 

@@ -208,6 +208,18 @@ int apgpu_calibrate_repair(const void* raw, int raw_kind, float pedestal, int ha
                            float* out, int out_big_endian, int64_t* counts, apgpu_stream_t stream);
 
 /* ------------------------------------------------------------------------
+ * Image arithmetic.  Replaces np.add / np.subtract / np.multiply / np.divide(data1, data2, out=result) of
+ * ApImArith.process_files, core/ApImArith.py:321-333, for a float32 image `a`:
+ *   b_kind 0  scalar (rounded to float32 first, as numpy treats a Python float), float32 arithmetic
+ *   b_kind 1  `b` is a float32 image, float32 arithmetic
+ *   b_kind 2  `b` is a float64 image: float64 arithmetic, result cast to float32
+ * Division by zero gives inf / NaN as in numpy.
+ * ---------------------------------------------------------------------- */
+enum { APGPU_OP_ADD = 0, APGPU_OP_SUB = 1, APGPU_OP_MUL = 2, APGPU_OP_DIV = 3 };
+int apgpu_imarith_f32(const float* a, const void* b, int b_kind, double scalar, int op,
+                      float* out, int64_t npix, apgpu_stream_t stream);
+
+/* ------------------------------------------------------------------------
  * Whole-image sigma-clipped statistics and threshold mask: the arithmetic of the
  * mask producer ApFindBadPixels._generate_sigmaclip_mask,
  * core/ApFindBadPixels.py:191-209.

@@ -208,6 +208,30 @@ def mint_combine_kat():
     print("combine_kat.npz")
 
 
+def mint_imarith():
+    """Inputs and the outputs of the reference's ApImArith.process_files executed verbatim."""
+    rng = np.random.default_rng(77)
+    shape = (23, 41)                        # odd sizes: vector body + scalar tail
+    a = rng.normal(2000, 300, shape).astype(np.float32)
+    a[0, :3] = [0.0, -0.0, np.inf]
+    b32 = rng.normal(10, 4, shape).astype(np.float32)
+    b32[1, :3] = [0.0, np.nan, -0.0]
+    b64 = rng.normal(10, 4, shape)
+    store = dict(a=a, b32=b32, b64=b64)
+    meta = []
+    for op in ("ADD", "SUB", "MUL", "DIV"):
+        for name, val in (("scalar", 3.3), ("scalar0", 0.0), ("b32", b32), ("b64", b64)):
+            out, hdr, hist = ref_exec.ref_imarith(a, op, val, units="adu/s" if op == "DIV" else None)
+            store[f"out_{op}_{name}"] = out
+            meta.append((op, name, str(out.dtype), hdr.get("BUNIT"), len(hist)))
+    out, hdr, hist = ref_exec.ref_imarith(a, " sub ", 1.5, hdr1={"PEDESTAL": -100, "BUNIT": "adu"})
+    store["out_ped"] = out
+    meta.append(("sub_ped", "scalar", str(out.dtype), hdr.get("BUNIT"), "PEDESTAL" in hdr))
+    store["meta_json"] = np.array(json.dumps(meta))
+    np.savez_compressed(os.path.join(GOLD, "imarith.npz"), **store)
+    print("imarith.npz", len(meta), "cases")
+
+
 ORDER_CASES = {
     # name: (generator, N, shape, seed, k_lo, k_hi, maxiters, cen, dev)
     "dark30_apmastercal": ("dark", 30, (64, 96), 0, 5.0, 5.0, 1, "median", "mad_std"),
@@ -251,6 +275,9 @@ def main():
     if "--order-census" in sys.argv:
         mint_order_census()
         return
+    if "--imarith" in sys.argv:
+        mint_imarith()
+        return
     if not ref_exec.reference_available():
         raise SystemExit("needs /root/reference (authoring container)")
     mint_calibrate()
@@ -258,6 +285,7 @@ def main():
     mint_findbadpix()
     mint_combine_kat()
     mint_order_census()
+    mint_imarith()
 
 
 if __name__ == "__main__":

@@ -111,6 +111,9 @@ class FakeHDUList(list):
             FakeHDU(None if h.data is None else np.array(h.data, copy=True),
                     h.header.copy()) for h in self)
 
+    def close(self):
+        pass
+
     def __enter__(self):
         return self
 
@@ -240,9 +243,13 @@ def _load():
         else __import__("pathlib").Path(filename).expanduser())
     # ApFindBadPixels._read_fits refers to ``sys`` without importing it
     # (core/ApFindBadPixels.py:302) -- only on the 3-D error path.
+    with _stubbed_modules():
+        arithmod = load("ApImArith")
+    arithmod.ApImArith._check_file_exists = lambda self, filename: None
     _loaded.update(ApFixBadPixels=fixmod.ApFixBadPixels,
                    ApFindBadPixels=findmod.ApFindBadPixels,
-                   ApCalibrate=calmod.ApCalibrate)
+                   ApCalibrate=calmod.ApCalibrate,
+                   ApImArith=arithmod.ApImArith)
     return _loaded
 
 
@@ -289,3 +296,29 @@ def ref_find_bad_pixels(dark, sigma, user_yaml_path=None, dark_hdr=None,
         if user_yaml_path is not None:
             obj.add_user_badpix(user_yaml_path)
     return obj.get_mask().copy(), obj._nbad_auto, obj._nbad_user
+
+
+def ref_imarith(data1, operation, value, hdr1=None, units=None, loglevel="ERROR"):
+    """Reference ``ApImArith.process_files`` (core/ApImArith.py:255-346) executed verbatim.  ``value`` is a
+    number (passed as its string, like the CLI does) or a second image (registered as an in-memory FITS file
+    behind a real temporary path, because the reference tests ``Path(value).exists()``).  Returns
+    ``(result ndarray, output header dict, history list)``."""
+    import tempfile
+    cls = _load()["ApImArith"]
+    FITS_STORE.clear()
+    put_image("in.fits", data1, hdr1)
+    tmp = None
+    if isinstance(value, np.ndarray):
+        tmp = tempfile.NamedTemporaryFile(suffix=".fits")
+        put_image(tmp.name, value)
+        value = tmp.name
+    else:
+        value = repr(float(value))
+    try:
+        with np.errstate(all="ignore"):
+            cls(loglevel).process_files("in.fits", operation, value, "out.fits", units)
+    finally:
+        if tmp is not None:
+            tmp.close()
+    out, hdr = get_image("out.fits")
+    return out, dict(hdr.items()), list(hdr.history)

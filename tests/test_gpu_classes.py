@@ -300,6 +300,37 @@ def test_calibrate_many_equals_per_frame_calibrate(cuda, tmp_path):
     assert ap_calibrate_all.main(argv) == 0 and os.path.getmtime(outdir / "cal-raw0.fits") == stamp      # skipped
 
 
+def test_float64_masters_are_cast_and_stay_within_1e6_of_the_float64_arithmetic(cuda, tmp_path):
+    """Documented deviation: masters written as float64 (what ccdproc.combine and ApMasterCal's default write)
+    make numpy promote the reference's whole calibration to float64; here they are cast to float32 on load and
+    the output is float32.  The result stays within float32 rounding of the float64 arithmetic: every operation
+    contributes at most one ulp of its operands (raw, bias, scaled dark), divided by the flat."""
+    import astrophotography_b200 as ap
+    from astrophotography_b200 import fitsio, synth
+    from oracle import calibrate_oracle as co
+    shape = (40, 56)
+    rng = np.random.default_rng(9)
+    bias64 = rng.normal(1000, 5, shape)
+    dark64 = rng.normal(1040, 6, shape)
+    flat64 = synth.flat_frame(shape).astype(np.float64)
+    raw = synth.science_frame(shape, nstars=3)
+    b = _fits(tmp_path / "b64.fits", bias64)
+    d = _fits(tmp_path / "d64.fits", dark64, EXPTIME=900.0)
+    f = _fits(tmp_path / "f64.fits", flat64)
+    r = _fits(tmp_path / "raw.fits", raw, EXPTIME=300.0)
+    ap.ApCalibrate(b, d, f, None, "ERROR", True).calibrate(r, str(tmp_path / "cal.fits"), 2, None, False)
+    got, _ = fitsio.read_image(tmp_path / "cal.fits", 0)
+    assert got.dtype == np.float32
+    nf64 = co.normalise_flat(flat64)
+    exp = co.calibrate(co.read_convert(raw), bias64, dark64, 300.0 / 900.0, nf64, True)
+    assert exp.dtype == np.float64                                     # what the reference would have written
+    ok = np.isfinite(exp) & np.isfinite(got) & (nf64 != 0)
+    scale = (np.abs(raw.astype(np.float64)) + 2 * np.abs(bias64) + np.abs(dark64)) / np.abs(np.where(ok, nf64, 1.0))
+    err = np.abs(got.astype(np.float64) - exp)
+    assert (err[ok] <= 4 * 2.0 ** -24 * scale[ok] + 1e-6 * np.abs(exp[ok])).all()
+    assert np.array_equal(np.isnan(got), np.isnan(exp))
+
+
 def test_master_keeps_pedestal_and_apcalibrate_removes_it(cuda, tmp_path):
     """MaximDL-style frames carry PEDESTAL=-100.  Like ccdproc.combine the master keeps the keyword (the
     frames are combined as stored) and ApCalibrate._read_fits removes the pedestal from the master bias /

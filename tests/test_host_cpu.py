@@ -331,7 +331,7 @@ def test_mastercal_file_checks(tmp_path):
 
 # ---------------------------------------------------------------- CLI surface
 @pytest.mark.parametrize("script,needle", [
-    ("ap_calibrate", "--dark_still_biased"), ("ap_fix_badpix", "--deltapix"), ("ap_calibrate_all", "--gpus"),
+    ("ap_calibrate", "--dark_still_biased"), ("ap_fix_badpix", "--deltapix"), ("ap_calibrate_all", "--gpus"), ("ap_imarith", "--units"),
     ("ap_find_badpix", "--user_badpix"), ("ap_combine_darks", "--temptol")])
 def test_cli_help(script, needle):
     r = subprocess.run([sys.executable, "-m", f"astrophotography_b200.scripts.{script}", "--help"],

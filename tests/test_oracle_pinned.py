@@ -133,6 +133,25 @@ def test_oracle_vs_live_reference_fix_dtypes():
             assert bits_equal(out, ref)
 
 
+def test_imarith_goldens_are_the_live_reference(golden_dir):
+    """tests/golden/imarith.npz was minted by running the reference's ApImArith.process_files verbatim; when the
+    reference tree is present the same call must reproduce it, and plain numpy must agree (the arithmetic is
+    four ufunc calls, core/ApImArith.py:321-333)."""
+    import json
+    z = np.load(os.path.join(golden_dir, "imarith.npz"))
+    a = z["a"]
+    for op, name, dtype, _b, _n in json.loads(str(z["meta_json"]))[:-1]:
+        val = {"scalar": 3.3, "scalar0": 0.0, "b32": z["b32"], "b64": z["b64"]}[name]
+        fn = {"ADD": np.add, "SUB": np.subtract, "MUL": np.multiply, "DIV": np.divide}[op]
+        res = np.zeros(a.shape, dtype=a.dtype)
+        with np.errstate(all="ignore"):
+            fn(a, val, out=res)
+        assert bits_equal(res, z[f"out_{op}_{name}"]), (op, name)
+        if ref_exec.reference_available():
+            out, _, _ = ref_exec.ref_imarith(a, op, val)
+            assert bits_equal(out, z[f"out_{op}_{name}"])
+
+
 # ---------------------------------------------------------------- combine (unpinned: KATs + numpy facts)
 def test_combine_oracle_hand_kats(golden_dir):
     k = np.load(os.path.join(golden_dir, "combine_kat.npz"))
