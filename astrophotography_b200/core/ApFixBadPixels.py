@@ -83,10 +83,13 @@ class ApFixBadPixels(ApBase):
                 self._logger.warning("Pixel medians may suffer from casting truncation because"
                                      f" the input data is not a floating point datatype ({orig_dtype}).")
             work = data if orig_dtype == np.float32 else data.astype(np.float32)
-            if orig_dtype not in (np.float32,) and not _exact_in_f32(data):
-                msg = (f"fix_bad_pixels: dtype {orig_dtype} values are not exactly representable in"
-                       " float32; only float32, 8/16-bit integer (and exactly representable) data"
-                       " are supported on the GPU path.")
+            if not _exact_in_f32(data):
+                # np.median's even-count mean (a + b) / 2 is a float64 operation for float64 / 32- and 64-bit
+                # integer data: float32 arithmetic could round differently, so those dtypes are refused
+                # rather than silently repaired with other last bits
+                msg = (f"fix_bad_pixels: dtype {orig_dtype} is not supported on the GPU path: only float32 and"
+                       " 8/16-bit integer data are repaired bit for bit like the reference (cast the image to"
+                       " float32 first if float32 medians are acceptable).")
                 self._logger.error(msg)
                 raise RuntimeError(msg)
             d_dev = torch.from_numpy(np.ascontiguousarray(work)).cuda()
@@ -129,10 +132,8 @@ def _stats_dict_impl(min_valid, npix, nbad, nfixed, deltapix):
 
 
 def _exact_in_f32(a):
-    if a.dtype in (np.uint8, np.int8, np.uint16, np.int16, np.bool_):
-        return True
-    with np.errstate(all="ignore"):
-        return bool(np.array_equal(a.astype(np.float32).astype(a.dtype), a, equal_nan=True))
+    """float32 data, and integers whose pairwise sums are exact in float32 (8 / 16 bits)."""
+    return a.dtype in (np.float32, np.uint8, np.int8, np.uint16, np.int16, np.bool_)
 
 
 def _mask_to_device(torch, mask, device):

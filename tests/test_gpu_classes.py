@@ -252,6 +252,25 @@ def test_make_master_overlaps_file_reads_with_uploads(cuda, tmp_path):
     assert t_files <= 1.3 * (t_read + t_comb)
 
 
+def test_fix_bad_pixels_refuses_dtypes_it_cannot_repair_exactly(cuda):
+    """float64 / 32-bit integer images: np.median's even-count mean is a float64 operation there, so the float32
+    kernel refuses them instead of returning other last bits; 16-bit integers are exact and truncate like numpy."""
+    import astrophotography_b200 as ap
+    from oracle import badpix_oracle as bo
+    rng = np.random.default_rng(2)
+    mask = (rng.random((24, 30)) < 0.05).astype(np.uint8)
+    fixer = ap.ApFixBadPixels("CRITICAL")
+    for dt in (np.float64, np.int32, np.int64):
+        with pytest.raises(RuntimeError, match="not supported on the GPU path"):
+            fixer.fix_bad_pixels(rng.normal(1000, 30, (24, 30)).astype(dt), mask, 2)
+    img = rng.integers(0, 60000, (24, 30)).astype(np.uint16)
+    got, _ = fixer.fix_bad_pixels(img, mask, 2)
+    # numpy assigns np.median's float64 result into the uint16 array by truncation (core/ApFixBadPixels.py:409);
+    # for 16-bit values the float32 median is the same number
+    expf, _ = bo.fix_bad_pixels_vec(img.astype(np.float32), mask, 2)
+    assert got.dtype == np.uint16 and np.array_equal(got, np.trunc(expf).astype(np.uint16))
+
+
 def test_calibrate_many_equals_per_frame_calibrate(cuda, tmp_path):
     """The batch driver (masters resident, three streams, fused calibrate + repair, FITS byte order produced on
     the GPU) writes the same pixels and keywords as one ApCalibrate.calibrate call per frame; the ap_calibrate_all
