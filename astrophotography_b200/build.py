@@ -45,6 +45,8 @@ SOURCES = ['stack_sorted_med_f32_p3.cu',
            'stack_sorted_medmad1_u16_p0.cu',
            'stack_sorted_medunc_f32_p0.cu',
            'stack_sorted_medunc_u16_p0.cu',
+           'stack_median_coop_p8.cu',
+           'stack_median_coop_p4.cu',
            'stack_meanclip_coop_p8.cu',
            'stack_meanclip_coop_p4.cu',
            'stack_meanclip_coop_p2.cu',

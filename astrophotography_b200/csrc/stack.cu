@@ -68,6 +68,12 @@ bool meanclip_eligible(int N, int method, double klo, double khi, int maxiters, 
            N >= 3 && klo > 0.0 && khi > 0.0 && klo < 1e6 && khi < 1e6;
 }
 
+// plain median of a long stack (no clipping, no uncertainty plane): the lane-cooperative kernel
+bool median_coop_eligible(int N, int method, int maxiters, bool want_uncert, int flags) {
+    return !(flags & APGPU_STACK_FORCE_GENERIC) && method == APGPU_METHOD_MEDIAN && maxiters == 0 && !want_uncert &&
+           N > 200 && N <= 512;
+}
+
 Family choose_family(int N, int method, double klo, double khi, int maxiters, int cen, int dev,
                      bool want_uncert, int flags, const Bucket** bucket) {
     *bucket = nullptr;
@@ -225,6 +231,10 @@ extern "C" const char* apgpu_stack_kernel_name(int N, int method, double k_lo, d
         else snprintf(g_kname, sizeof(g_kname), "meanclip_split<8>");
         return g_kname;
     }
+    if (median_coop_eligible(N, method, maxiters, want_uncert != 0, flags)) {
+        snprintf(g_kname, sizeof(g_kname), "median_coop<%d>", N <= 256 ? 4 : 8);
+        return g_kname;
+    }
     switch (f) {
         case FAM_MEANCLIP: snprintf(g_kname, sizeof(g_kname), "meanclip<%d>", b->nb); break;
         case FAM_MEANCLIP_SMEM: snprintf(g_kname, sizeof(g_kname), "meanclip_smem"); break;
@@ -288,6 +298,21 @@ int stack_reduce_impl(const T* const* frames, int u16_format, int N, int64_t H, 
         if (N > 100 && meanclip_eligible(N, method, k_lo, k_hi, maxiters, cen, dev, flags)) {
             int64_t done = 0;
             const int rc = stack_dispatch_meanclip_split(frames, a, st, flags, &done);
+            if (rc != APGPU_OK && rc != APGPU_ERR_UNSUPPORTED) return rc;
+            if (rc == APGPU_OK) {
+                a.pix0 += done;
+                a.npix -= done;
+                if (a.npix == 0) return APGPU_OK;
+            }
+        }
+    }
+    // long plain medians on equally spaced float32 frames: lane-cooperative selection (stack_median_coop.cuh)
+    if constexpr (sizeof(T) == sizeof(float)) {
+        if (median_coop_eligible(N, method, maxiters, out_uncert != nullptr, flags) &&
+            stack_is_cube(frames, N, a.pix0 + a.npix)) {
+            int64_t done = 0;
+            const int rc = N <= 256 ? stack_dispatch_median_coop_p4(frames, a, st, &done)
+                                    : stack_dispatch_median_coop_p8(frames, a, st, &done);
             if (rc != APGPU_OK && rc != APGPU_ERR_UNSUPPORTED) return rc;
             if (rc == APGPU_OK) {
                 a.pix0 += done;

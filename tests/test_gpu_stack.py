@@ -557,3 +557,32 @@ def test_u16_row_bands_and_staging(cuda, n, row0, nrows):
     _assert_close_data(data[band].astype(np.float64), exp["data"][band], RTOL32, 12.0)
     keep = np.ones(shape[0], bool); keep[band] = False
     assert (data[keep] == -7.0).all() and (nrej[keep] == 255).all()
+
+
+# ---------------------------------------------------------------- long medians: lane-cooperative selection
+@pytest.mark.parametrize("n", [201, 202, 224, 225, 255, 256, 257, 300, 320, 321, 383, 384, 400, 448, 449, 511, 512])
+@pytest.mark.parametrize("quantise", [False, True])
+def test_long_median_lane_cooperative(cuda, n, quantise):
+    """200 < N <= 512: 4 or 8 lanes sort a share of the samples each and select the median of the union of their
+    sorted runs -- comparison-only, bit-exact (ties from quantised data, NaN / inf pixels via the generic routine,
+    a tail shorter than a 32-pixel tile)."""
+    torch = cuda
+    from astrophotography_b200 import kernels
+    assert kernels.stack_kernel_name(n, "median", maxiters=0).startswith("median_coop")
+    st = _stack(n, (7, 76), seed=500 + n, quantise=quantise)            # 532 pixels: 16 tiles + a 20-pixel tail
+    if quantise:
+        st[:, 2, :] = np.rint(st[:, 2, :] / 8) * 8                      # many equal samples around the median
+    exp = _oracle(st, "median", 5.0, 5.0, 0, "median", "mad_std")
+    for out_f64 in (False, True):
+        got = _run(torch, st, method="median", maxiters=0, out_f64=out_f64)
+        assert kernels.stack_last_staging() == 5
+        e = exp["data"] if out_f64 else exp["data"].astype(np.float32)
+        assert bits_equal(got["data"], e), (n, np.argwhere(got["data"] != e)[:5])
+        assert np.array_equal(got["nrej"].astype(np.int64), exp["nrej"])
+    # a row band that does not start on a 16-byte boundary falls back to the generic kernel, same answer
+    cube = torch.from_numpy(st).cuda()
+    out = {"data": torch.full((7, 76), -7.0, dtype=torch.float32, device="cuda")}
+    kernels.stack_reduce(cube, method="median", maxiters=0, row0=1, nrows=5, out=out, want_nrej=False)
+    torch.cuda.synchronize()
+    d = out["data"].cpu().numpy()
+    assert bits_equal(d[1:6], exp["data"][1:6].astype(np.float32)) and (d[0] == -7.0).all() and (d[6] == -7.0).all()
