@@ -45,8 +45,12 @@ SOURCES = ['stack_sorted_med_f32_p3.cu',
            'stack_sorted_medmad1_u16_p0.cu',
            'stack_sorted_medunc_f32_p0.cu',
            'stack_sorted_medunc_u16_p0.cu',
-           'stack_median_coop_p8.cu',
-           'stack_median_coop_p4.cu',
+           'stack_median_coop_medunc_p8.cu',
+           'stack_median_coop_medunc_p4.cu',
+           'stack_median_coop_medmad1_p8.cu',
+           'stack_median_coop_medmad1_p4.cu',
+           'stack_median_coop_med_p8.cu',
+           'stack_median_coop_med_p4.cu',
            'stack_meanclip_coop_p8.cu',
            'stack_meanclip_coop_p4.cu',
            'stack_meanclip_coop_p2.cu',

@@ -68,10 +68,14 @@ bool meanclip_eligible(int N, int method, double klo, double khi, int maxiters, 
            N >= 3 && klo > 0.0 && khi > 0.0 && klo < 1e6 && khi < 1e6;
 }
 
-// plain median of a long stack (no clipping, no uncertainty plane): the lane-cooperative kernel
-bool median_coop_eligible(int N, int method, int maxiters, bool want_uncert, int flags) {
-    return !(flags & APGPU_STACK_FORCE_GENERIC) && method == APGPU_METHOD_MEDIAN && maxiters == 0 && !want_uncert &&
-           N > 200 && N <= 512;
+// long stacks on the lane-cooperative sorted kernels: -1 = not eligible, else MODE_MED (plain median),
+// MODE_MEDUNC (median + uncertainty plane) or MODE_MEDMAD1 (one median/MAD clip pass, then the mean)
+int median_coop_mode(int N, int method, int maxiters, int cen, int dev, bool want_uncert, int flags) {
+    if ((flags & APGPU_STACK_FORCE_GENERIC) || N <= 200 || N > 512) return -1;
+    if (method == APGPU_METHOD_MEDIAN && maxiters == 0) return want_uncert ? MODE_MEDUNC : MODE_MED;
+    if (method == APGPU_METHOD_AVERAGE && maxiters == 1 && cen == APGPU_CEN_MEDIAN && dev == APGPU_DEV_MAD_STD)
+        return MODE_MEDMAD1;
+    return -1;
 }
 
 Family choose_family(int N, int method, double klo, double khi, int maxiters, int cen, int dev,
@@ -231,8 +235,10 @@ extern "C" const char* apgpu_stack_kernel_name(int N, int method, double k_lo, d
         else snprintf(g_kname, sizeof(g_kname), "meanclip_split<8>");
         return g_kname;
     }
-    if (median_coop_eligible(N, method, maxiters, want_uncert != 0, flags)) {
-        snprintf(g_kname, sizeof(g_kname), "median_coop<%d>", N <= 256 ? 4 : 8);
+    const int cmode = median_coop_mode(N, method, k_lo == k_lo ? maxiters : maxiters, cen, dev, want_uncert != 0, flags);
+    if (cmode >= 0) {
+        snprintf(g_kname, sizeof(g_kname), "%s_coop<%d>", cmode == MODE_MED ? "median" : (cmode == MODE_MEDUNC ? "median_mad" : "medmad1"),
+                 N <= 256 ? 4 : 8);
         return g_kname;
     }
     switch (f) {
@@ -308,11 +314,16 @@ int stack_reduce_impl(const T* const* frames, int u16_format, int N, int64_t H, 
     }
     // long plain medians on equally spaced float32 frames: lane-cooperative selection (stack_median_coop.cuh)
     if constexpr (sizeof(T) == sizeof(float)) {
-        if (median_coop_eligible(N, method, maxiters, out_uncert != nullptr, flags) &&
-            stack_is_cube(frames, N, a.pix0 + a.npix)) {
+        const int cmode = median_coop_mode(N, method, maxiters, cen, dev, out_uncert != nullptr, flags);
+        if (cmode >= 0 && stack_is_cube(frames, N, a.pix0 + a.npix)) {
             int64_t done = 0;
-            const int rc = N <= 256 ? stack_dispatch_median_coop_p4(frames, a, st, &done)
-                                    : stack_dispatch_median_coop_p8(frames, a, st, &done);
+            int rc;
+            if (cmode == MODE_MED)
+                rc = N <= 256 ? stack_dispatch_median_coop_med_p4(frames, a, st, &done) : stack_dispatch_median_coop_med_p8(frames, a, st, &done);
+            else if (cmode == MODE_MEDUNC)
+                rc = N <= 256 ? stack_dispatch_median_coop_medunc_p4(frames, a, st, &done) : stack_dispatch_median_coop_medunc_p8(frames, a, st, &done);
+            else
+                rc = N <= 256 ? stack_dispatch_median_coop_medmad1_p4(frames, a, st, &done) : stack_dispatch_median_coop_medmad1_p8(frames, a, st, &done);
             if (rc != APGPU_OK && rc != APGPU_ERR_UNSUPPORTED) return rc;
             if (rc == APGPU_OK) {
                 a.pix0 += done;

@@ -359,8 +359,11 @@ int stack_dispatch_meanclip_coop_p2(const float* const* frames, const StackArgs&
 int stack_dispatch_meanclip_coop_p4(const float* const* frames, const StackArgs& a, cudaStream_t st, int64_t* done_pix);
 int stack_dispatch_meanclip_coop_p8(const float* const* frames, const StackArgs& a, cudaStream_t st, int64_t* done_pix);
 // lane-cooperative median (200 < N <= 512, equally spaced float32 frames): same contract
-int stack_dispatch_median_coop_p4(const float* const* frames, const StackArgs& a, cudaStream_t st, int64_t* done_pix);
-int stack_dispatch_median_coop_p8(const float* const* frames, const StackArgs& a, cudaStream_t st, int64_t* done_pix);
+#define APGPU_DECL_MEDCOOP(m) \
+    int stack_dispatch_median_coop_##m##_p4(const float* const* frames, const StackArgs& a, cudaStream_t st, int64_t* done_pix); \
+    int stack_dispatch_median_coop_##m##_p8(const float* const* frames, const StackArgs& a, cudaStream_t st, int64_t* done_pix);
+APGPU_DECL_MEDCOOP(med) APGPU_DECL_MEDCOOP(medunc) APGPU_DECL_MEDCOOP(medmad1)
+#undef APGPU_DECL_MEDCOOP
 // sorted<NB, NLO, MODE> kernels (stack_sorted.cuh).  One translation unit per (mode, sample type, bucket part):
 // the unrolled networks are slow to compile (10-25 s per bucket), so the explicit instantiations
 // dispatch_sorted_part<MODE, T, PART> are spread over many files that nvcc compiles in parallel.

@@ -1,4 +1,5 @@
-// Frame-stack reducer: lane-cooperative median for long stacks (200 < N <= 512) on equally spaced frames.
+// Frame-stack reducer: lane-cooperative median, median + uncertainty and median/MAD clip for long stacks
+// (200 < N <= 512) on equally spaced frames.
 // See stack_common.cuh / stack_sorted.cuh / stack_meanclip_coop.cuh.
 //
 // One thread cannot hold more than ~200 samples, and round 1 sent every median beyond 200 frames to the generic
@@ -13,8 +14,12 @@
 //      shared memory how many elements of its window are < v and <= v, the group sums the counts (butterfly of
 //      shuffles) and all windows shrink to one side of v -- or v is the answer.  Comparison-only, exact, 3-4
 //      rounds with the interpolated proposal; for even N the successor (rank k1 + 1) is the smallest element above the answer over all runs.
-// The median is therefore bit-exact like the single-thread network.  Pixels holding NaN / inf go to the generic
-// routine, which owns the reference's non-finite semantics.
+//   4. (MEDUNC / MEDMAD1) the MAD is a second selection of the same kind over the 2P deviation lists the sorted
+//      runs split into at the median, in float64 like the oracle; the clip bounds then cut every run by binary
+//      search and the kept ranges are summed per lane and across the lanes.
+// The median is therefore bit-exact like the single-thread network, rejection counts are the oracle's, clipped
+// means within a few ulp (lane-partial float64 sums).  Pixels holding NaN / inf go to the generic routine, which
+// owns the reference's non-finite semantics.
 #pragma once
 #include "stack_meanclip_coop.cuh"
 #include "stack_sorted.cuh"
@@ -34,7 +39,22 @@ __host__ __device__ constexpr int medcoop_min_blocks(int NBL, int P) {
     return P == 8 ? (NBL <= 40 ? 3 : 2) : 4;
 }
 
-template <int NBL, int P>
+// double-precision group reductions (the float ones live in LaneGroup)
+template <int P> __device__ __forceinline__ double group_min(double v) {
+#pragma unroll
+    for (int o = 32 / P; o < 32; o <<= 1) { const double w = __shfl_xor_sync(0xffffffffu, v, o); v = w < v ? w : v; }
+    return v;
+}
+
+// first index in [lo, hi) at which pred(i) is false (pred is true on a prefix)
+template <typename Pred> __device__ __forceinline__ int partition_point(int lo, int hi, Pred pred) {
+    while (lo < hi) { const int m = (lo + hi) >> 1; if (pred(m)) lo = m + 1; else hi = m; }
+    return lo;
+}
+
+// MODE_MED: plain median.  MODE_MEDUNC: median + 1.4826 * MAD / sqrt(N).  MODE_MEDMAD1: one median/MAD clip pass,
+// then the mean of the kept samples (the reference's ApMasterCal setting).
+template <int NBL, int P, int MODE>
 __global__ void __launch_bounds__(coop_tpb(P), medcoop_min_blocks(NBL, P))
 stack_median_coop_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CubeFrames cube,
                          const __grid_constant__ StackArgs a) {
@@ -167,6 +187,95 @@ stack_median_coop_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
             const float nxt = LG::min((!nonfinite && b0 < nreal) ? *elem(b0) : INFINITY, FULL);
             second = (n_le > k1 + 1) ? ans : nxt;
         }
+        const double med = (N & 1) ? (double)ans : __dmul_rn(__dadd_rn((double)ans, (double)second), 0.5);
+        double out_val = med, out_unc = (double)NAN;
+        int out_nrej = 0;
+        if constexpr (MODE != MODE_MED) {
+            // ---- MAD: the rank-k1 (and k1+1) smallest of |x - med| over the union of the runs.  Every run splits
+            // at the median into two lists with ascending deviations: L[j] = med - run[s-1-j], R[j] = run[s+j] - med
+            // (float64, rounded like the oracle's np.abs(x - med)); the same windowed selection runs over 2P lists.
+            const int s0 = nonfinite ? 0 : partition_point(0, nreal, [&](int i) { return (double)*elem(i) < med; });
+            const int nL = s0, nR = nonfinite ? 0 : nreal - s0;
+            auto devL = [&](int j) { return fabs(__dsub_rn((double)*elem(s0 - 1 - j), med)); };
+            auto devR = [&](int j) { return fabs(__dsub_rn((double)*elem(s0 + j), med)); };
+            int loL = 0, hiL = nL, loR = 0, hiR = nR;
+            kk = k1;
+            bool fnd = nonfinite;
+            double d1 = 0.0;
+            for (int round = 0; round <= NB; ++round) {
+                if (!__any_sync(FULL, !fnd)) break;
+                const int szL = fnd ? 0 : hiL - loL, szR = fnd ? 0 : hiR - loR;
+                const int side = szR > szL ? 1 : 0;
+                int key = ((side ? szR : szL) << 5) | (side << 4) | (15 - r);
+#pragma unroll
+                for (int o = PIXW; o < 32; o <<= 1) key = max(key, __shfl_xor_sync(FULL, key, o));
+                const int rstar = 15 - (key & 15), sstar = (key >> 4) & 1;
+                const int total = LG::sum(szL + szR, FULL);
+                double v = 0.0;
+                if (!fnd && r == rstar) {
+                    const int wl = sstar ? loR : loL, wh = sstar ? hiR : hiL;
+                    int pos = wl + ((2 * kk + 1) * (wh - wl)) / (2 * max(total, 1));
+                    pos = min(max(pos, wl), wh - 1);
+                    v = sstar ? devR(pos) : devL(pos);
+                }
+                v = __shfl_sync(FULL, v, rstar * PIXW + q);
+                int ltL = loL, leL = loL, ltR = loR, leR = loR;
+                if (!fnd) {
+                    ltL = partition_point(loL, hiL, [&](int j) { return devL(j) < v; });
+                    leL = ltL;
+                    while (leL < hiL && devL(leL) <= v) ++leL;
+                    ltR = partition_point(loR, hiR, [&](int j) { return devR(j) < v; });
+                    leR = ltR;
+                    while (leR < hiR && devR(leR) <= v) ++leR;
+                }
+                const int t_lt = LG::sum((ltL - loL) + (ltR - loR), FULL);
+                const int t_le = LG::sum((leL - loL) + (leR - loR), FULL);
+                if (!fnd) {
+                    if (kk < t_lt) { hiL = ltL; hiR = ltR; }
+                    else if (kk < t_le) { fnd = true; d1 = v; }
+                    else { loL = leL; loR = leR; kk -= t_le; }
+                }
+            }
+            double d2 = d1;
+            if (!(N & 1)) {
+                const int ubL = nonfinite ? 0 : partition_point(0, nL, [&](int j) { return devL(j) <= d1; });
+                const int ubR = nonfinite ? 0 : partition_point(0, nR, [&](int j) { return devR(j) <= d1; });
+                const int n_le = LG::sum(ubL + ubR, FULL);
+                double nx = (double)INFINITY;
+                if (!nonfinite && ubL < nL) nx = devL(ubL);
+                if (!nonfinite && ubR < nR) { const double t = devR(ubR); nx = t < nx ? t : nx; }
+                nx = group_min<P>(nx);
+                d2 = (n_le > k1 + 1) ? d1 : nx;
+            }
+            const double mad = (N & 1) ? d1 : __dmul_rn(__dadd_rn(d1, d2), 0.5);
+            const double sd = __dmul_rn(MAD_TO_STD, mad);
+            if constexpr (MODE == MODE_MEDUNC) {
+                out_unc = __ddiv_rn(sd, __dsqrt_rn((double)N));        // Combiner.median_combine: mad_std / sqrt(n)
+            } else {
+                // ---- one clip pass, then the mean of the kept range of every run (float64 partial sums per lane,
+                // butterfly across the lanes: within a few ulp of the oracle's frame-order sum)
+                const double lo_b = __dsub_rn(med, __dmul_rn(sd, a.klo));
+                const double hi_b = __dadd_rn(med, __dmul_rn(sd, a.khi));
+                const int sa = nonfinite ? 0 : partition_point(0, nreal, [&](int i) { return (double)*elem(i) < lo_b; });
+                const int sb = nonfinite ? 0 : partition_point(sa, nreal, [&](int i) { return !((double)*elem(i) > hi_b); });
+                const int nk = LG::sum(sb - sa, FULL);
+                double acc = 0.0;
+                for (int i = sa; i < sb; ++i) acc = __dadd_rn(acc, (double)*elem(i));
+                acc = LG::sum(acc, FULL);
+                const double mean = __ddiv_rn(acc, (double)(nk > 0 ? nk : 1));   // nk >= 1: the median itself survives
+                out_val = mean;
+                out_nrej = N - nk;
+                if (a.uncert) {
+                    double qq = 0.0;
+                    for (int i = sa; i < sb; ++i) {
+                        const double d = __dsub_rn((double)*elem(i), mean);
+                        qq = __dadd_rn(qq, __dmul_rn(d, d));
+                    }
+                    qq = LG::sum(qq, FULL);
+                    out_unc = __ddiv_rn(__dsqrt_rn(__ddiv_rn(qq, (double)(nk > 0 ? nk : 1))), __dsqrt_rn((double)(nk > 0 ? nk : 1)));
+                }
+            }
+        }
         // this warp is done with the stage: the last warp of the group re-arms it for the group's next tile
         const int next = tile + G;
         __syncwarp();
@@ -184,17 +293,13 @@ stack_median_coop_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
         __syncwarp();
         if (r == 0) {
             const int64_t p = (int64_t)(uint32_t)(pix0 + tile * 32 + col);
-            if (nonfinite) {
-                generic_pixel<NB, CubeFrames>(cube, a, p);
-            } else {
-                const double med = (N & 1) ? (double)ans : __dmul_rn(__dadd_rn((double)ans, (double)second), 0.5);
-                write_pixel(a, p, med, 0, (double)NAN, 0);
-            }
+            if (nonfinite) generic_pixel<NB, CubeFrames>(cube, a, p);
+            else write_pixel(a, p, out_val, out_nrej, out_unc, 0);
         }
     }
 }
 
-template <int NBL, int P>
+template <int NBL, int P, int MODE>
 int launch_median_coop(const float* const* frames, const StackArgs& a_in, cudaStream_t st, int64_t* done_pix) {
     constexpr int NB = NBL * P;
     constexpr int G = (coop_tpb(P) / 32) / P;
@@ -215,10 +320,10 @@ int launch_median_coop(const float* const* frames, const StackArgs& a_in, cudaSt
         return APGPU_ERR_UNSUPPORTED;
     CubeFrames cube{(const char*)frames[0], stride};
     const size_t smem = (size_t)G * NB * 128 + G * (sizeof(uint64_t) + sizeof(int)) + 1024;   // + alignment slack
-    APGPU_CUDA(cudaFuncSetAttribute(stack_median_coop_kernel<NBL, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    APGPU_CUDA(cudaFuncSetAttribute(stack_median_coop_kernel<NBL, P, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t run = (int64_t)G * a.tiles_per_warp;
     const int64_t grid = (ntiles + run - 1) / run;
-    stack_median_coop_kernel<NBL, P><<<(unsigned)grid, coop_tpb(P), smem, st>>>(tmap, cube, a);
+    stack_median_coop_kernel<NBL, P, MODE><<<(unsigned)grid, coop_tpb(P), smem, st>>>(tmap, cube, a);
     APGPU_LAUNCH_CHECK("stack_median_coop_kernel");
     *done_pix = ntiles * 32;
     stack_note_staging(5);
@@ -226,6 +331,6 @@ int launch_median_coop(const float* const* frames, const StackArgs& a_in, cudaSt
 }
 
 #define MEDCOOP_CASE(NBL_, NLO_, P_) \
-    if (a.N > NLO_ && a.N <= NBL_ * P_) return launch_median_coop<NBL_, P_>(frames, a, st, done_pix);
+    if (a.N > NLO_ && a.N <= NBL_ * P_) return launch_median_coop<NBL_, P_, MEDCOOP_MODE>(frames, a, st, done_pix);
 
 }  // namespace apgpu_stack

@@ -586,3 +586,36 @@ def test_long_median_lane_cooperative(cuda, n, quantise):
     torch.cuda.synchronize()
     d = out["data"].cpu().numpy()
     assert bits_equal(d[1:6], exp["data"][1:6].astype(np.float32)) and (d[0] == -7.0).all() and (d[6] == -7.0).all()
+
+
+@pytest.mark.parametrize("n", [201, 224, 256, 257, 300, 384, 449, 512])
+@pytest.mark.parametrize("quantise", [False, True])
+def test_long_medmad_and_median_uncertainty_lane_cooperative(cuda, n, quantise):
+    """200 < N <= 512: the reference's median/MAD clip and the median with its uncertainty plane on the
+    lane-cooperative kernels (MAD = a second rank selection over the deviation lists of the sorted runs, float64
+    like the oracle): rejection maps identical, medians bit-exact, means within a few ulp."""
+    torch = cuda
+    from astrophotography_b200 import kernels
+    assert kernels.stack_kernel_name(n).startswith("medmad1_coop")
+    assert kernels.stack_kernel_name(n, "median", maxiters=0, want_uncert=True).startswith("median_mad_coop")
+    st = _stack(n, (7, 76), seed=700 + n, quantise=quantise)
+    if quantise:
+        st[:, 2, :] = np.rint(st[:, 2, :] / 8) * 8                      # many ties in samples and deviations
+    for k_lo, k_hi in ((5.0, 5.0), (1.5, 2.5)):
+        exp = _oracle(st, "average", k_lo, k_hi, 1, "median", "mad_std")
+        for out_f64 in (False, True):
+            got = _run(torch, st, method="average", k_lo=k_lo, k_hi=k_hi, maxiters=1, cen="median", dev="mad_std",
+                       out_f64=out_f64, want_uncert=True)
+            assert kernels.stack_last_staging() == 5
+            assert np.array_equal(got["nrej"].astype(np.int64), exp["nrej"]), (n, k_lo)
+            assert np.array_equal(got["allmasked"], exp["allmasked"])
+            _assert_close_data(got["data"].astype(np.float64), exp["data"], RTOL32 if not out_f64 else 1e-13, 12.0)
+            _assert_close_data(got["uncert"].astype(np.float64), exp["uncert"], 1e-5 if not out_f64 else 1e-12, 1e-3)
+    expm = _oracle(st, "median", 5.0, 5.0, 0, "median", "mad_std")
+    for out_f64 in (False, True):
+        got = _run(torch, st, method="median", maxiters=0, out_f64=out_f64, want_uncert=True)
+        assert kernels.stack_last_staging() == 5
+        e = expm["data"] if out_f64 else expm["data"].astype(np.float32)
+        assert bits_equal(got["data"], e)
+        ok = np.isfinite(expm["uncert"]) & np.isfinite(st).all(axis=0)
+        _assert_close_data(got["uncert"].astype(np.float64)[ok], expm["uncert"][ok], 1e-6 if not out_f64 else 1e-14, 1e-3)

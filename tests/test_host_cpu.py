@@ -49,7 +49,9 @@ def test_kernel_selection_is_host_logic():
     assert kernels.stack_kernel_name(30, "median", maxiters=0, want_uncert=True) == "sorted_median_mad<32>"
     assert kernels.stack_kernel_name(300, "median", maxiters=0) == "median_coop<8>"
     assert kernels.stack_kernel_name(256, "median", maxiters=0) == "median_coop<4>"
-    assert kernels.stack_kernel_name(300, "median", maxiters=0, want_uncert=True).startswith("generic")
+    assert kernels.stack_kernel_name(300, "median", maxiters=0, want_uncert=True) == "median_mad_coop<8>"
+    assert kernels.stack_kernel_name(250) == "medmad1_coop<4>" and kernels.stack_kernel_name(513).startswith("generic")
+    assert kernels.stack_kernel_name(300, "average", 3, 3, 5, "median", "std").startswith("generic")
     assert kernels.stack_kernel_name(600, "median", maxiters=0).startswith("generic")
     assert kernels.stack_kernel_name(30, force_generic=True).startswith("generic")
     assert kernels.stack_kernel_name(600, "average", 3, 3, 5, "mean", "std") == "meanclip_split<8>"
