@@ -94,7 +94,13 @@ def test_full_frame_cmos_stack_200x9576x6388_config4(cuda):
         for rank in range(world):
             r0, r1, _, _ = pipeline.row_band(h, world, rank)
             kernels.stack_reduce(cube, row0=r0, nrows=r1 - r0, out=out, **p)
-        assert torch.equal(out["data"], res["data"]) and torch.equal(out["nrej"], res["nrej"])
+        # rejection maps identical; the means are bit-identical except in each band's < 32-pixel tail, which the
+        # register kernel reduces instead of the lane-cooperative one (another float32 summation order: ~1e-8)
+        assert torch.equal(out["nrej"], res["nrej"])
+        diff = out["data"] != res["data"]
+        assert int(diff.sum()) <= 32 * world
+        d = (out["data"].double() - res["data"].double()).abs()
+        assert bool((d <= 2e-7 * res["data"].double().abs().clamp_min(12.0)).all())
     del cube
 
 
