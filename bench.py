@@ -383,6 +383,11 @@ def run_gpu(args, shape):
                     lambda: kernels.fix_badpix(kernels.calibrate(raw, bias, dark, nflat, 1.0 / 3.0, True, out=cal), mask, 2),
                     mpix, 27 * h * w, steps=5, unit="Mpix/s")
         del raw, flat, nflat, cal, mask
+        # the batch driver end to end through FILES (rank 0): ApCalibrate.calibrate_many (masters resident, three
+        # streams, fused calibrate + repair, FITS byte order produced on the GPU) against one ApCalibrate.calibrate
+        # call per frame with the same resident masters; 4096 x 4096 uint16 frames in a temporary directory
+        if rank == 0 and not args.small:
+            variants.update(batch_driver_variant(torch, device))
 
     # ---- end to end through the host-buffer API (pinned host frames) ----
     e2e = None
@@ -539,6 +544,52 @@ def run_gpu(args, shape):
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def batch_driver_variant(torch, device, nframes=8, shape=(4096, 4096)):
+    import shutil
+    import tempfile
+    import astrophotography_b200 as ap
+    from astrophotography_b200 import fitsio, synth
+    tmp = tempfile.mkdtemp(prefix="apgpu_bench_")
+    try:
+        rng = np.random.default_rng(3)
+        hdr = fitsio.new_header
+        fitsio.write_image(os.path.join(tmp, "mbias.fits"), rng.normal(1000, 5, shape).astype(np.float32), hdr({}))
+        fitsio.write_image(os.path.join(tmp, "mdark.fits"), rng.normal(1040, 6, shape).astype(np.float32), hdr({"EXPTIME": 900.0}))
+        fitsio.write_image(os.path.join(tmp, "mflat.fits"), synth.flat_frame(shape), hdr({}))
+        fitsio.write_image(os.path.join(tmp, "mask.fits"), synth.badpix_mask(shape, auto_fraction=1e-3), hdr({}))
+        raws = []
+        base = synth.science_frame(shape, nstars=20)
+        for k in range(nframes):
+            path = os.path.join(tmp, f"raw{k}.fits")
+            fitsio.write_image(path, np.roll(base, 17 * k, axis=1), hdr({"EXPTIME": 300.0, "PEDESTAL": -100}))
+            raws.append(path)
+        cal = ap.ApCalibrate(os.path.join(tmp, "mbias.fits"), os.path.join(tmp, "mdark.fits"), os.path.join(tmp, "mflat.fits"),
+                             os.path.join(tmp, "mask.fits"), "ERROR", True)
+        outs = [os.path.join(tmp, f"cal{k}.fits") for k in range(nframes)]
+        cal.calibrate_many(raws[:2], outs[:2], 2)                     # warm-up (page cache, pinned buffers)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        cal.calibrate_many(raws, outs, 2)
+        torch.cuda.synchronize()
+        t_many = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for r, o in zip(raws, outs):
+            cal.calibrate(r, o, 2, None, False)
+        torch.cuda.synchronize()
+        t_one = time.perf_counter() - t0
+        mpix = shape[0] * shape[1] / 1e6
+        note = f"{nframes} uint16 frames of {shape[1]}x{shape[0]} read from and written to FITS files in a temporary directory"
+        return {
+            "batch_driver_calibrate_many_files": {"value": nframes / t_many, "unit": "frames/s", "ms": 1e3 * t_many / nframes,
+                                                  "mpix_per_s": nframes * mpix / t_many, "note": note},
+            "per_frame_calibrate_files_same_resident_masters": {"value": nframes / t_one, "unit": "frames/s",
+                                                                "ms": 1e3 * t_one / nframes, "mpix_per_s": nframes * mpix / t_one,
+                                                                "note": note},
+        }
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
 
 
 def _release_pinned_cache(torch):
