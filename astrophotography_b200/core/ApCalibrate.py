@@ -326,6 +326,15 @@ class ApCalibrate(ApBase):
         perf_time_start = time.perf_counter()
         raw_image = Path(raw_image)
         ext_num = 0
+        if not fixcosmic:
+            # the common case runs through the batch driver's frame path (raw FITS data unit straight to the GPU,
+            # one fused calibrate + repair call, FITS byte order produced on the device): same pixels, same keywords
+            self.calibrate_many([raw_image], [cal_image], delta_pix, ring=1)
+            if norm_flat is not None and self._norm_flat_dev is not None:
+                self._logger.debug(f"Writing normalized flat field to {norm_flat}")
+                self._write_image_like(raw_image, ext_num, norm_flat, self.norm_flat, {}, f"Processed by {self._name}")
+            self._logger.info(f"Wrote bias/dark/flat corrected file to {cal_image}")
+            return
         raw_data, raw_hdr, pedestal = self._read_fits(raw_image, ext_num, to_float=False)
         if raw_data.dtype != np.uint16:
             # anything but the common unsigned 16-bit frame takes the reference's
