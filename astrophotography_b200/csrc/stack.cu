@@ -257,6 +257,10 @@ extern "C" int apgpu_stack_last_staging(void) { return g_last_staging; }
 namespace apgpu_stack {
 
 template <typename T>
+int stack_reduce_fast(const T* const* frames, int N, double k_lo, double k_hi, int flags, StackArgs a, cudaStream_t st,
+                      void* out_uncert, bool* used_fast);
+
+template <typename T>
 int stack_reduce_impl(const T* const* frames, int u16_format, int N, int64_t H, int64_t W,
                       int64_t row0, int64_t nrows, int method,
                       double k_lo, double k_hi, int maxiters, int cen, int dev,
@@ -296,6 +300,23 @@ int stack_reduce_impl(const T* const* frames, int u16_format, int N, int64_t H, 
     for (int i = 0; i < MEANCLIP_MAX_TAIL; ++i) a.tailmask[i] = 0.f;
     cudaStream_t st = (cudaStream_t)stream;
     g_last_staging = -1;
+    bool used_fast = false;
+    const int rc = stack_reduce_fast<T>(frames, N, k_lo, k_hi, flags, a, st, out_uncert, &used_fast);
+    if (rc != APGPU_OK || !used_fast) return rc;
+    // the pixels the fast kernels left marked (non-finite samples, guard-band hits): generic routine
+    static const bool skip_marked = getenv("APGPU_SKIP_MARKED") != nullptr;      // diagnostic knob (tools/count_marks.py)
+    if (skip_marked) return APGPU_OK;
+    static const bool twice = getenv("APGPU_MARKED_TWICE") != nullptr;          // diagnostic: the second launch is the pure scan
+    if (twice) stack_launch_marked(frames, a, st);
+    return stack_launch_marked(frames, a, st);
+}
+
+template <typename T>
+int stack_reduce_fast(const T* const* frames, int N, double k_lo, double k_hi, int flags, StackArgs a, cudaStream_t st,
+                      void* out_uncert, bool* used_fast) {
+    const int method = a.method, maxiters = a.maxiters, cen = a.cen, dev = a.dev;
+    const int64_t pix0_call = a.pix0;
+    *used_fast = true;
 
     // long stacks on equally spaced frames: the lane-split tensor-map kernels take every full warp tile,
     // whatever follows only sees the (< 32-pixel) tail  (float32 frames; uint16 frames use the register
@@ -348,7 +369,10 @@ int stack_reduce_impl(const T* const* frames, int u16_format, int N, int64_t H, 
         case FAM_SORT_MEDMAD1: return stack_dispatch_sorted<MODE_MEDMAD1, T>(N, frames, a, st);
         default: break;
     }
-    return stack_launch_generic(frames, a, st);
+    // (a generic launch over the remaining range leaves no marks of its own; earlier fast launches may have)
+    const int rcg = stack_launch_generic(frames, a, st);
+    if (a.pix0 == pix0_call) *used_fast = false;
+    return rcg;
 }
 
 }  // namespace apgpu_stack

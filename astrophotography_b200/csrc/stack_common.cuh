@@ -125,6 +125,30 @@ __device__ __forceinline__ void write_pixel(const StackArgs& a, int64_t p, doubl
     if (a.allmasked) a.allmasked[p] = (uint8_t)allm;
 }
 
+// Pixels a fast kernel cannot finish (non-finite samples, a survivor inside the float32 guard band, everything
+// rejected) are MARKED instead of being finished in place: a NaN with a payload no result can carry goes to the
+// output image, all-ones to the rejection map, and stack_launch_marked() -- one small launch after the fast
+// kernels of the call -- scans for the marks and runs generic_pixel on exactly those pixels.  Calling the generic
+// routine from inside the fast kernels cost them a stack frame, spills around the call and, in the
+// lane-cooperative kernels, stalled the whole tile group for the 30-300 us the routine takes (measured: 7 % of
+// the N = 100 kappa-sigma kernel, two thirds of the N = 512 one).
+// (the low 4 bits of the payload say why -- read by tools/count_marks.py with APGPU_SKIP_MARKED=1)
+constexpr uint32_t STACK_MARK32 = 0x7fc5a5a0u;
+constexpr uint64_t STACK_MARK64 = 0x7ff85a5a5a5a5a50ull;
+enum { MARK_NONFINITE = 1, MARK_BOUNDS = 2, MARK_BAND = 3, MARK_EMPTY = 4 };
+__device__ __forceinline__ void mark_pixel(const StackArgs& a, int64_t p, int why = 0) {
+    if (a.out_f64) reinterpret_cast<uint64_t*>(a.out)[p] = STACK_MARK64 | (uint64_t)why;
+    else reinterpret_cast<uint32_t*>(a.out)[p] = STACK_MARK32 | (uint32_t)why;
+    if (a.nrej) {
+        if (a.nrej_u16) reinterpret_cast<uint16_t*>(a.nrej)[p] = 0xffffu;
+        else reinterpret_cast<uint8_t*>(a.nrej)[p] = 0xffu;
+    }
+}
+__device__ __forceinline__ bool pixel_is_marked(const StackArgs& a, int64_t p) {
+    return a.out_f64 ? (reinterpret_cast<const uint64_t*>(a.out)[p] & ~(uint64_t)15) == STACK_MARK64
+                     : (reinterpret_cast<const uint32_t*>(a.out)[p] & ~15u) == STACK_MARK32;
+}
+
 // ---------------------------------------------------------------------------
 // generic routine: float64, oracle operation order
 // ---------------------------------------------------------------------------
@@ -342,6 +366,9 @@ int stack_median_tiles_per_cta();
 // cross-translation-unit launchers (one .cu per kernel family so that nvcc compiles them in parallel)
 int stack_launch_generic(const float* const* frames, const StackArgs& a, cudaStream_t st);
 int stack_launch_generic(const uint16_t* const* frames, const StackArgs& a, cudaStream_t st);
+// finish the pixels the fast kernels marked in [a.pix0, a.pix0 + a.npix) (see mark_pixel)
+int stack_launch_marked(const float* const* frames, const StackArgs& a, cudaStream_t st);
+int stack_launch_marked(const uint16_t* const* frames, const StackArgs& a, cudaStream_t st);
 int stack_dispatch_meanclip_lo(int nb, const float* const* frames, const StackArgs& a, cudaStream_t st, int flags);
 int stack_dispatch_meanclip_mid(int nb, const float* const* frames, const StackArgs& a, cudaStream_t st, int flags);
 int stack_dispatch_meanclip_hi(int nb, const float* const* frames, const StackArgs& a, cudaStream_t st, int flags);

@@ -168,13 +168,14 @@ __device__ __forceinline__ void meanclip_pixel(float2 (&y)[NB / 2], const Frames
     // generic routine owns those semantics.
     const bool nonfinite = !(S2 <= FLT_MAX) || !(fabsf(S1) <= FLT_MAX);
     if constexpr (P == 1) {
-        if (nonfinite) { generic_pixel<CAPG, Frames>(fp, a, p); return; }
+        if (nonfinite) { mark_pixel(a, p, MARK_NONFINITE); return; }
     }
 
     int nk = N;
     const float klo = (float)a.klo, khi = (float)a.khi;
     const float kmax = fmaxf(klo, khi);
     bool uncertain = nonfinite;
+    int why = 0;                                       // (diagnostic: payload of the mark)
     int it = 0;
     // Sums after a rejection are updated by SUBTRACTING the rejected samples' contributions
     // while that is accurate (what is left of sum(y^2) is at least half of the last fully
@@ -329,7 +330,7 @@ __device__ __forceinline__ void meanclip_pixel(float2 (&y)[NB / 2], const Frames
             if (S2 == 0.f) break;            // all survivors equal the pivot: bounds [c,c], nothing to reject
             Bounds B;
             const int st = make_bounds(B);
-            if (st == 1) { uncertain = true; break; }
+            if (st == 1) { uncertain = true; why = MARK_BOUNDS; break; }
             if (st == 2) break;              // converged, no pass needed
             uint64_t flags = 0;
             float M_nf = 0.f;
@@ -340,7 +341,7 @@ __device__ __forceinline__ void meanclip_pixel(float2 (&y)[NB / 2], const Frames
             rare_pass(B, flags, r1, r2, nrej_it, vmax, vmin);
             nk -= nrej_it;
             // a survivor inside the guard band: float64 must decide
-            if (!(vmin > B.ylo_in && vmax < B.yhi_in)) { uncertain = true; break; }
+            if (!(vmin > B.ylo_in && vmax < B.yhi_in)) { uncertain = true; why = MARK_BAND; break; }
             if (nk == 0) break;
             M_prev = fmaxf(M_nf, fmaxf(vmax - B.c, B.c - vmin)) * 1.000001f;
             c_prev = B.c;
@@ -358,7 +359,7 @@ __device__ __forceinline__ void meanclip_pixel(float2 (&y)[NB / 2], const Frames
                 nsub = 0;
             }
         }
-        if (uncertain || nk == 0) { generic_pixel<CAPG, Frames>(fp, a, p); return; }
+        if (uncertain || nk == 0) { mark_pixel(a, p, nonfinite ? MARK_NONFINITE : (nk == 0 ? MARK_EMPTY : why)); return; }
     } else {
         // P lanes per pixel: the loop is WARP-uniform (every lane stays in it until the warp's last
         // pixel is done, finished pixels idle through it) so that the butterflies are full-mask
@@ -377,7 +378,7 @@ __device__ __forceinline__ void meanclip_pixel(float2 (&y)[NB / 2], const Frames
                     done = true;
                 } else {
                     const int st = make_bounds(B);
-                    if (st == 1) { uncertain = true; done = true; }
+                    if (st == 1) { uncertain = true; why = MARK_BOUNDS; done = true; }
                     else if (st == 2) done = true;
                     else pass = true;
                 }
@@ -396,7 +397,7 @@ __device__ __forceinline__ void meanclip_pixel(float2 (&y)[NB / 2], const Frames
             bool need_resum = false;
             if (pass) {
                 nk -= nrej_it;
-                if (!(vmin > B.ylo_in && vmax < B.yhi_in)) { uncertain = true; done = true; }
+                if (!(vmin > B.ylo_in && vmax < B.yhi_in)) { uncertain = true; why = MARK_BAND; done = true; }
                 else if (nk == 0) done = true;
                 else {
                     M_prev = fmaxf(M_nf, fmaxf(vmax - B.c, B.c - vmin)) * 1.000001f;
@@ -437,7 +438,7 @@ __device__ __forceinline__ void meanclip_pixel(float2 (&y)[NB / 2], const Frames
     }
     if constexpr (P > 1) {
         if (r != 0) return;
-        if (uncertain || nk == 0) { generic_pixel<CAPG, Frames>(fp, a, p); return; }
+        if (uncertain || nk == 0) { mark_pixel(a, p, nonfinite ? MARK_NONFINITE : (nk == 0 ? MARK_EMPTY : why)); return; }
     }
     const double cy = __ddiv_rn(sum1, (double)nk);
     // (uint16 frames are staged as 2^23 + value: pivot - sample_bias is the pivot's value, exactly)

@@ -55,7 +55,7 @@ stack_meanclip_smem_kernel(const __grid_constant__ FramePtrs<CAP> fp, const __gr
             }
         }
     }
-    if (!(S2 <= FLT_MAX) || !(fabsf(S1) <= FLT_MAX)) { generic_pixel<CAP>(fp, a, p); return; }
+    if (!(S2 <= FLT_MAX) || !(fabsf(S1) <= FLT_MAX)) { mark_pixel(a, p); return; }
 
     int nk = N;
     const float klo = (float)a.klo, khi = (float)a.khi;
@@ -125,7 +125,7 @@ stack_meanclip_smem_kernel(const __grid_constant__ FramePtrs<CAP> fp, const __gr
         S2 = n2;
         if (nk == nk_before || nk == 0) break;
     }
-    if (uncertain || nk == 0) { generic_pixel<CAP>(fp, a, p); return; }
+    if (uncertain || nk == 0) { mark_pixel(a, p); return; }
 
     double sum1 = (double)S1, sum2 = (double)S2;
     if (a.out_f64) {

@@ -293,7 +293,7 @@ stack_median_coop_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
         __syncwarp();
         if (r == 0) {
             const int64_t p = (int64_t)(uint32_t)(pix0 + tile * 32 + col);
-            if (nonfinite) generic_pixel<NB, CubeFrames>(cube, a, p);
+            if (nonfinite) mark_pixel(a, p);
             else write_pixel(a, p, out_val, out_nrej, out_unc, 0);
         }
     }

@@ -158,7 +158,7 @@ stack_sorted_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
         sort_regs<NB, MIX>(x, a.one, a.minus_one);
         [&]() {
             if (!valid) return;
-            if (nonfinite) { generic_pixel<NB, FramePtrs<NB, T>>(fp, a, p); return; }
+            if (nonfinite) { mark_pixel(a, p); return; }
 
             constexpr int C = NB / 2;
             const double med = (N & 1) ? (double)x[C - 1]
@@ -267,7 +267,7 @@ stack_median_tmap_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
         const int p = pix0 + tile * STPB + threadIdx.x;
         if (p < pend) {
             if (z != z) {
-                generic_pixel<NB, FramePtrs<NB, T>>(fp, a, (int64_t)p);
+                mark_pixel(a, (int64_t)p);
             } else {
                 constexpr int C = NB / 2;
                 const double med = (N & 1) ? (double)x[C - 1]
