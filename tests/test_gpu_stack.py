@@ -619,3 +619,66 @@ def test_long_medmad_and_median_uncertainty_lane_cooperative(cuda, n, quantise):
         assert bits_equal(got["data"], e)
         ok = np.isfinite(expm["uncert"]) & np.isfinite(st).all(axis=0)
         _assert_close_data(got["uncert"].astype(np.float64)[ok], expm["uncert"][ok], 1e-6 if not out_f64 else 1e-14, 1e-3)
+
+
+# ---------------------------------------------------------------------------
+# marked pixels: what the fast kernels cannot finish is redone by the scan launch (csrc/stack_generic.cu)
+# ---------------------------------------------------------------------------
+MARK_LAYOUTS = {"f32+u8": dict(out_f64=False, want_nrej=True),
+                "f64+uncert+counts": dict(out_f64=True, want_nrej=True, want_uncert=True),
+                "f32 alone": dict(out_f64=False, want_nrej=False),
+                "f64 alone": dict(out_f64=True, want_nrej=False)}
+MARK_PARAMS = {"kappa": dict(method="average", k_lo=3.0, k_hi=3.0, maxiters=5, cen="mean", dev="std"),
+               "plain mean": dict(method="average", k_lo=3.0, k_hi=3.0, maxiters=0, cen="mean", dev="std"),
+               "medmad": dict(method="average", k_lo=5.0, k_hi=5.0, maxiters=1, cen="median", dev="mad_std"),
+               "median": dict(method="median", k_lo=3.0, k_hi=3.0, maxiters=0, cen="mean", dev="std")}
+
+
+@pytest.mark.parametrize("n", [20, 100, 256, 300])
+@pytest.mark.parametrize("layout", list(MARK_LAYOUTS))
+@pytest.mark.parametrize("params", list(MARK_PARAMS))
+def test_marked_pixels_are_finished_by_the_scan_launch(cuda, n, layout, params):
+    """Many pixels with NaN / inf samples (each is marked by the fast kernel), constant pixels with one NaN (the
+    warp-cooperative float64 routine gives up on sd = 0 and hands over to the generic one), an odd width and a row
+    band that starts off every 16-byte boundary, with and without a rejection map to scan."""
+    torch = cuda
+    from astrophotography_b200 import kernels
+    h, w, row0, nrows = 37, 203, 3, 29
+    st = _stack(n, (h, w), seed=11)
+    rng = np.random.default_rng(n)
+    flat = st.reshape(n, -1)
+    for value, frac in ((np.nan, 0.10), (np.inf, 0.02), (-np.inf, 0.01)):
+        px = np.flatnonzero(rng.random(h * w) < frac)
+        flat[rng.integers(0, n, px.size), px] = value
+    flat[:, 5 * w + 7] = np.nan                                   # nothing left
+    flat[:, 6 * w + 9] = 5.0
+    flat[n // 3, 6 * w + 9] = np.nan                              # constant but for one NaN
+    kw, lay = MARK_PARAMS[params], MARK_LAYOUTS[layout]
+    exp = _oracle(st, kw["method"], kw["k_lo"], kw["k_hi"], kw["maxiters"], kw["cen"], kw["dev"])
+    cube = torch.from_numpy(st).cuda()
+    dt = torch.float64 if lay["out_f64"] else torch.float32
+    out = {"data": torch.full((h, w), -1.0, dtype=dt, device="cuda")}
+    if lay["want_nrej"]:
+        out["nrej"] = torch.full((h, w), 7, dtype=torch.uint16 if n > 255 else torch.uint8, device="cuda")
+    res = kernels.stack_reduce(cube, row0=row0, nrows=nrows, out=out, want_allmasked=True, **kw, **lay)
+    torch.cuda.synchronize()
+    band = slice(row0, row0 + nrows)
+    d = res["data"].cpu().numpy().astype(np.float64)
+    assert (d[:row0] == -1).all() and (d[row0 + nrows:] == -1).all()
+    if params == "median":
+        e = exp["data"][band] if lay["out_f64"] else exp["data"][band].astype(np.float32).astype(np.float64)
+        _assert_close_data(d[band], e, 0.0, 1.0)
+    else:
+        _assert_close_data(d[band], exp["data"][band], 1e-12 if lay["out_f64"] and params == "medmad" else RTOL32, 1.0)
+    # no mark survives: the marks are NaNs with a payload in the low mantissa bits
+    raw = res["data"].view(torch.int64 if lay["out_f64"] else torch.int32).cpu().numpy()
+    nan_bits = raw[np.isnan(res["data"].cpu().numpy())]
+    assert np.all((nan_bits & 0xfffff) == 0)
+    if lay["want_nrej"]:
+        nr = res["nrej"].cpu().numpy().astype(np.int64)
+        assert np.array_equal(nr[band], exp["nrej"][band])
+        assert (nr[:row0] == 7).all() and (nr[row0 + nrows:] == 7).all()
+    assert np.array_equal(res["allmasked"].cpu().numpy()[band] != 0, exp["allmasked"][band] != 0)
+    if lay.get("want_uncert"):
+        u = res["uncert"].cpu().numpy().astype(np.float64)
+        _assert_close_data(u[band], exp["uncert"][band], 1e-6, 1e-3)
