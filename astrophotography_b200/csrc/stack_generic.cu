@@ -38,6 +38,7 @@ int launch_generic_any(const T* const* frames, const StackArgs& a, cudaStream_t 
 // the launch costs the scan: ~1 / (4N) of the stack's bytes.
 constexpr int MK_THREADS = 256;
 constexpr int MK_UNROLL = 4;
+constexpr int MK_LIST = 2048;       // marks a CTA collects before its warps share them out
 
 // which of the 16 / ES elements of the vector could be marks (bit e = element e)?
 template <int ES> __device__ __forceinline__ unsigned vector_mark_candidates(const uint4 v) {
@@ -161,6 +162,8 @@ stack_marked_kernel(const __grid_constant__ FramePtrs<CAP, T> fp, const __grid_c
     const int64_t pend = a.pix0 + a.npix;
     const int lane = threadIdx.x & 31;
     __shared__ float parked[WARP ? MK_THREADS / 32 : 1][WARP ? APGPU_STACK_MAX_FRAMES : 1];
+    __shared__ uint32_t list[WARP ? MK_LIST : 1];
+    __shared__ int nlist;
     auto finish = [&](int64_t p) {                      // WARP: called by all lanes with the same p
         if (p >= a.pix0 && p < pend && pixel_is_marked(a, p)) {
             if constexpr (WARP) {
@@ -180,6 +183,15 @@ stack_marked_kernel(const __grid_constant__ FramePtrs<CAP, T> fp, const __grid_c
     for (int64_t p = a.pix0 + unit; p < first_vec_pix; p += nunits) finish(p);
     for (int64_t p = tail0 + unit; p < pend; p += nunits) finish(p);
     const uint4* const vecs = reinterpret_cast<const uint4*>(plane + first_vec_pix * ES);
+    // WARP: the marks go to the CTA's shared-memory list while it scans, and its warps share them out once the
+    // scan is done -- one mark takes a warp ~10 us of dependent latencies (is-it-marked load, sample loads, a
+    // few float64 iterations), so what matters is how many marks the unluckiest warp ends up with: finishing
+    // them where they are found left ~5 on one warp where the average is 0.5 (measured 100 us for the 5300 marks
+    // of the 100 x 61 Mpixel stack; sharing out after EVERY sweep, with CTA barriers in the loop: 147 us).
+    if constexpr (WARP) {
+        if (threadIdx.x == 0) nlist = 0;
+        __syncthreads();
+    }
     for (int64_t b = tid - lane; b < nvec; b += nthreads * MK_UNROLL) {      // (warp-uniform trip count)
         uint4 v[MK_UNROLL];
 #pragma unroll
@@ -190,23 +202,31 @@ stack_marked_kernel(const __grid_constant__ FramePtrs<CAP, T> fp, const __grid_c
 #pragma unroll
         for (int u = 0; u < MK_UNROLL; ++u) {
             unsigned cand = vector_mark_candidates<ES>(v[u]);
+            const int64_t p0 = first_vec_pix + (b + lane + (int64_t)u * nthreads) * EPV;
             if constexpr (WARP) {
-                // (sharing a CTA's marks out among its warps through a shared-memory list was measured: slower,
-                // 147 us against 101 us for the 5300 marks of the 100 x 61 Mpixel stack -- the CTA barriers cost
-                // more than the unluckiest warp's extra marks)
+                while (cand) {
+                    const int slot = atomicAdd(&nlist, 1);
+                    if (slot >= MK_LIST) break;             // list full: the rest is finished in place
+                    list[slot] = (uint32_t)(p0 + (__ffs((int)cand) - 1));
+                    cand &= cand - 1;
+                }
                 unsigned hits = __ballot_sync(0xffffffffu, cand != 0u);
                 while (hits) {
                     const int src = __ffs((int)hits) - 1;
                     hits &= hits - 1;
-                    const int64_t p0 = first_vec_pix + (b + src + (int64_t)u * nthreads) * EPV;
+                    const int64_t q0 = __shfl_sync(0xffffffffu, p0, src);
                     unsigned c = __shfl_sync(0xffffffffu, cand, src);
-                    while (c) { finish(p0 + (__ffs((int)c) - 1)); c &= c - 1; }
+                    while (c) { finish(q0 + (__ffs((int)c) - 1)); c &= c - 1; }
                 }
             } else {
-                const int64_t p0 = first_vec_pix + (b + lane + (int64_t)u * nthreads) * EPV;
                 while (cand) { finish(p0 + (__ffs((int)cand) - 1)); cand &= cand - 1; }
             }
         }
+    }
+    if constexpr (WARP) {
+        __syncthreads();
+        const int n = nlist < MK_LIST ? nlist : MK_LIST;
+        for (int k = threadIdx.x >> 5; k < n; k += MK_THREADS / 32) finish((int64_t)list[k]);
     }
 }
 
