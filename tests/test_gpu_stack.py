@@ -682,3 +682,27 @@ def test_marked_pixels_are_finished_by_the_scan_launch(cuda, n, layout, params):
     if lay.get("want_uncert"):
         u = res["uncert"].cpu().numpy().astype(np.float64)
         _assert_close_data(u[band], exp["uncert"][band], 1e-6, 1e-3)
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 8, 9, 30, 31, 64, 99, 100, 128, 200])
+@pytest.mark.parametrize("k", [(5.0, 5.0), (3.0, 3.0), (1.5, 4.0), (0.25, 0.5)])
+def test_medmad_tie_heavy_stacks(cuda, n, k):
+    """Median/MAD clip on few-valued integer samples (deviations tie with each other and with the clip bounds,
+    MAD = 0 where more than half of the samples agree), narrow and asymmetric clip factors (most pixels DO reject),
+    float32 and float64 + uncertainty outputs."""
+    torch = cuda
+    rng = np.random.default_rng(100 * n + int(10 * k[0]))
+    h, w = 24, 512                                               # whole 256-pixel tiles and 16-byte groups
+    st = rng.integers(0, 4, size=(n, h, w)).astype(np.float32) + 100.0
+    st[:, :8] = rng.normal(1000.0, 12.0, size=(n, 8, w)).astype(np.float32)
+    hits = rng.random((n, h, w)) < 0.01
+    st[hits] += 5000.0
+    st[:, 9, :7] = 42.0                                          # constant pixels
+    st[0, 9, :3] = 43.0                                          # ... but for one sample
+    exp = _oracle(st, "average", k[0], k[1], 1, "median", "mad_std")
+    for lay in ({"out_f64": True, "want_uncert": True}, {"out_f64": False}):
+        got = _run(torch, st, method="average", k_lo=k[0], k_hi=k[1], **lay)
+        assert np.array_equal(got["nrej"].astype(np.int64), exp["nrej"]), (n, k, lay)
+        _assert_close_data(got["data"].astype(np.float64), exp["data"], 1e-13 if lay["out_f64"] else RTOL32, 1.0)
+        if lay.get("want_uncert"):
+            _assert_close_data(got["uncert"], exp["uncert"], 1e-12, 1e-6)
