@@ -69,6 +69,11 @@ uint64_t apgpu_launch_count(void);
  *             APGPU_STACK_PREFER_SHARED: override the default choice between the
  *             register-resident and shared-memory-resident fast kernels
  * Limits: 1 <= N <= 1024.
+ * One call is a short sequence of launches on `stream`: the kernel(s) of the chosen
+ * family, then -- unless the generic kernel did everything -- a scan launch that redoes
+ * the few pixels a fast kernel could not finish (non-finite samples, float32 guard-band
+ * hits).  Between the two, those pixels hold a marker (a payload NaN in out_data, all
+ * ones in out_nrej): outputs are complete when the work queued on `stream` is.
  * ---------------------------------------------------------------------- */
 enum { APGPU_METHOD_MEDIAN = 0, APGPU_METHOD_AVERAGE = 1, APGPU_METHOD_MIN = 2, APGPU_METHOD_MAX = 3 };
 enum { APGPU_CEN_MEAN = 0, APGPU_CEN_MEDIAN = 1 };
