@@ -16,8 +16,8 @@
 //   meanclip<NB,NLO>    iterative kappa-sigma clip about the MEAN with the population STD,
 //                       then the mean of the survivors.  Register-resident, float32 arithmetic
 //                       on pivot-shifted values with a rigorous error bound: a pixel whose
-//                       decision could differ from the float64 oracle is redone by the generic
-//                       routine, so rejection maps are identical.  Fed by a warp-granular
+//                       decision could differ from the float64 oracle is MARKED and redone in
+//                       float64 by the scan launch below, so rejection maps are identical.  Fed by a warp-granular
 //                       tensor-map TMA pipeline when the frames are equally spaced
 //                       (stack_meanclip.cuh), else by direct loads / cp.async.
 //   meanclip_coop<NBL,P> the same algorithm for 100 < N <= 512: P lanes share a pixel, P warps
@@ -28,8 +28,11 @@
 //                       reference's ApMasterCal setting -- one median/MAD clip pass then the
 //                       mean (MODE_MEDMAD1) -- with the sorted column parked in shared memory
 //                       for the data-dependent MAD selection (stack_sorted.cuh).
-//   A pixel holding NaN/inf samples leaves the fast kernels for the generic
-//   routine, which owns the reference's non-finite semantics.
+//   marked              what a fast kernel cannot finish -- non-finite samples (the generic routine owns the
+//                       reference's NaN / inf semantics), float32 guard-band hits, everything rejected -- is
+//                       marked in the outputs (stack_common.cuh: mark_pixel) and one scan launch after the fast
+//                       kernels of the call (stack_generic.cu: stack_marked_kernel) redoes exactly those pixels:
+//                       warp-cooperative float64 for the kappa-sigma family, generic routine otherwise.
 #include <stdlib.h>
 
 #include "stack_common.cuh"

@@ -161,11 +161,14 @@ stack_marked_kernel(const __grid_constant__ FramePtrs<CAP, T> fp, const __grid_c
     constexpr int EPV = 16 / ES;                        // elements (pixels) per vector
     const int64_t pend = a.pix0 + a.npix;
     const int lane = threadIdx.x & 31;
-    __shared__ float parked[WARP ? MK_THREADS / 32 : 1][WARP ? APGPU_STACK_MAX_FRAMES : 1];
+    __shared__ float parked[WARP ? MK_THREADS / 32 : 1][WARP ? CAP : 1];       // (N <= CAP)
     __shared__ uint32_t list[WARP ? MK_LIST : 1];
     __shared__ int nlist;
-    auto finish = [&](int64_t p) {                      // WARP: called by all lanes with the same p
-        if (p >= a.pix0 && p < pend && pixel_is_marked(a, p)) {
+    // all-ones in the rejection map can only be a mark when the count cannot reach it (N < 255 / 65535): no need
+    // to confirm it against the output image then (one dependent load less per mark)
+    const bool sure = !(ES == 1 && a.N >= 255);          // (ES 4 / 8: the candidate test IS the mark test)
+    auto finish = [&](int64_t p, bool known) {          // WARP: called by all lanes with the same p
+        if (p >= a.pix0 && p < pend && (known || pixel_is_marked(a, p))) {
             if constexpr (WARP) {
                 if (!meanstd_pixel_warp(fp, a, p, lane, parked[threadIdx.x >> 5]) && lane == 0)
                     generic_pixel<CAP, FramePtrs<CAP, T>>(fp, a, p);
@@ -180,8 +183,8 @@ stack_marked_kernel(const __grid_constant__ FramePtrs<CAP, T> fp, const __grid_c
     // the pixels before the first and after the last whole aligned vector
     const int64_t tail0 = first_vec_pix + nvec * EPV;
     const int64_t unit = WARP ? (tid >> 5) : tid, nunits = WARP ? (nthreads >> 5) : nthreads;
-    for (int64_t p = a.pix0 + unit; p < first_vec_pix; p += nunits) finish(p);
-    for (int64_t p = tail0 + unit; p < pend; p += nunits) finish(p);
+    for (int64_t p = a.pix0 + unit; p < first_vec_pix; p += nunits) finish(p, false);
+    for (int64_t p = tail0 + unit; p < pend; p += nunits) finish(p, false);
     const uint4* const vecs = reinterpret_cast<const uint4*>(plane + first_vec_pix * ES);
     // WARP: the marks go to the CTA's shared-memory list while it scans, and its warps share them out once the
     // scan is done -- one mark takes a warp ~10 us of dependent latencies (is-it-marked load, sample loads, a
@@ -216,17 +219,17 @@ stack_marked_kernel(const __grid_constant__ FramePtrs<CAP, T> fp, const __grid_c
                     hits &= hits - 1;
                     const int64_t q0 = __shfl_sync(0xffffffffu, p0, src);
                     unsigned c = __shfl_sync(0xffffffffu, cand, src);
-                    while (c) { finish(q0 + (__ffs((int)c) - 1)); c &= c - 1; }
+                    while (c) { finish(q0 + (__ffs((int)c) - 1), sure); c &= c - 1; }
                 }
             } else {
-                while (cand) { finish(p0 + (__ffs((int)cand) - 1)); cand &= cand - 1; }
+                while (cand) { finish(p0 + (__ffs((int)cand) - 1), sure); cand &= cand - 1; }
             }
         }
     }
     if constexpr (WARP) {
         __syncthreads();
         const int n = nlist < MK_LIST ? nlist : MK_LIST;
-        for (int k = threadIdx.x >> 5; k < n; k += MK_THREADS / 32) finish((int64_t)list[k]);
+        for (int k = threadIdx.x >> 5; k < n; k += MK_THREADS / 32) finish((int64_t)list[k], sure);
     }
 }
 

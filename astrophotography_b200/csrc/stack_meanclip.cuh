@@ -111,7 +111,7 @@ template <int P> struct LaneGroup {
 //
 // NB samples per lane; with P > 1 lanes per pixel the stack holds up to NB * P frames, NLO is the
 // bucket's lower bound on the TOTAL frame count, `pivot_in` the pixel's pivot, `gmask` the lanes of
-// the pixel and `r` this lane's index among them (only r == 0 writes / runs the generic fallback).
+// the pixel and `r` this lane's index among them (only r == 0 writes or marks the pixel).
 template <int NB, int NLO, bool SYM, typename AfterSums = NoHook, int P = 1, typename Frames = FramePtrs<NB>,
           typename IMap = InterleavedFrames<P>>
 __device__ __forceinline__ void meanclip_pixel(float2 (&y)[NB / 2], const Frames& fp,
@@ -121,7 +121,6 @@ __device__ __forceinline__ void meanclip_pixel(float2 (&y)[NB / 2], const Frames
                                                const int r = 0) {
     static_assert(NB % 2 == 0, "meanclip buckets must be even");
     using G = LaneGroup<P>;
-    constexpr int CAPG = NB * P;                       // capacity of the generic fallback
     const int N = a.N;
     constexpr int NP = NB / 2;                         // register pairs
     constexpr int GP = 4;                              // pairs (8 samples) per group

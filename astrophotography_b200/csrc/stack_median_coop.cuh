@@ -18,7 +18,7 @@
 //      runs split into at the median, in float64 like the oracle; the clip bounds then cut every run by binary
 //      search and the kept ranges are summed per lane and across the lanes.
 // The median is therefore bit-exact like the single-thread network, rejection counts are the oracle's, clipped
-// means within a few ulp (lane-partial float64 sums).  Pixels holding NaN / inf go to the generic routine, which
+// means within a few ulp (lane-partial float64 sums).  Pixels holding NaN / inf are marked for the generic routine (stack_marked_kernel), which
 // owns the reference's non-finite semantics.
 #pragma once
 #include "stack_meanclip_coop.cuh"

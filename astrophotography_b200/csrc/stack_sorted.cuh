@@ -18,7 +18,7 @@ constexpr int STPB = 256;         // threads per CTA of the sorted kernels (lock
 // lo = fminf(a, b) is one of the two inputs bit for bit, so hi = bits(a) + bits(b) - bits(lo) in wrapping
 // integer arithmetic IS the other input, exactly (two IMAD on the FMA pipe; the multipliers +1 / -1 come
 // from the kernel arguments so that ptxas cannot fold them back into ALU-pipe IADD3).  Pixels holding a
-// NaN leave for the generic routine anyway.
+// NaN are marked for the generic routine anyway.
 __device__ __forceinline__ int imad_fma_pipe(int a, int m, int c) {
     int d;
     asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(m), "r"(c));
