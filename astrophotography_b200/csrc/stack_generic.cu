@@ -84,16 +84,21 @@ __device__ __forceinline__ int warp_sum(int v) {
 // loop -- this code runs cold, one warp at a time, where instruction fetch costs more than the arithmetic (an
 // unrolled register-resident version took 40 us per pixel, the generic routine with its serial loads and
 // local-memory arrays 100-300 us).  Partial sums are combined by butterfly.  That is another summation order than
-// the oracle's frame order; both are within ~N 2^-53 relative of the real-number value, so a sample further than
-// g = 2^-34 (1 + k)(|mean| + sd) from a clip bound is decided identically -- inside that band (probability ~1e-10
-// per pixel) the routine gives up (returns false) and the caller runs generic_pixel.
+// the oracle's frame order; both are within N 2^-53 (|mean| + sd) of the real-number mean / deviation (the oracle's
+// sequential sum is the looser of the two), a clip bound within (1 + k) times that, so a sample further than
+// g = 16 N 2^-53 (1 + k)(|mean| + sd) from a bound is decided identically -- inside that band the routine gives up
+// (returns false) and the caller runs generic_pixel.  The band must be that narrow: a marked pixel is one with a
+// sample within the FLOAT32 guard band of a bound, so the chance that it also lies within g is g over that band's
+// width -- with g = 2^-34 (...) it was 5e-4, i.e. 3 of the headline stack's 5300 marks and 6 of the N = 512 stack's
+// 12600 went to the generic routine, single-lane, and that one call WAS the duration of the launch (0.08 ms at
+// N = 100, 0.85 ms at N = 512: ncu source view, profiles/r02_ncu_meanclip_coop512.txt).
 template <typename Frames>
-__device__ __noinline__ bool meanstd_pixel_warp(const Frames& fp, const StackArgs& a, const int64_t p, const int lane,
+__device__ __forceinline__ bool meanstd_pixel_warp(const Frames& fp, const StackArgs& a, const int64_t p, const int lane,
                                                 float* __restrict__ x) {
     const int N = a.N;
     const bool clip = a.maxiters != 0;
     int nk = 0;
-#pragma unroll 4
+#pragma unroll 8
     for (int i = lane; i < N; i += 32) {
         const float v = load_sample(fp.frame(i) + p, a);
         // sigma_clip drops non-finite samples up front; without clipping the nan-functions only skip NaN
@@ -125,7 +130,7 @@ __device__ __noinline__ bool meanstd_pixel_warp(const Frames& fp, const StackArg
             const double sd = std_kept(nk, avg);
             const double lo = __dsub_rn(avg, __dmul_rn(sd, a.klo));
             const double hi = __dadd_rn(avg, __dmul_rn(sd, a.khi));
-            const double g = (1.0 + fmax(a.klo, a.khi)) * (fabs(avg) + sd) * 5.8207660913467407e-11;   // 2^-34
+            const double g = (1.0 + fmax(a.klo, a.khi)) * (fabs(avg) + sd) * ((double)N * 1.7763568394002505e-15);   // N 2^-49
             const double lo_out = lo - g, lo_in = lo + g, hi_in = hi - g, hi_out = hi + g;
             bool inband = !(g == g) || !(lo_in <= hi_in);
             int changed = 0;
