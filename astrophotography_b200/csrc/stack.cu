@@ -118,7 +118,9 @@ int stack_dispatch_meanclip_split(const float* const* frames, const StackArgs& a
         // lanes per pixel (measured, tools/time_variant.py): short per-lane arrays (<= 64 samples) keep the
         // unrolled code and the register count small, which matters more than the extra shuffle steps
         static const int force_p = getenv("APGPU_COOP_P") ? atoi(getenv("APGPU_COOP_P")) : 0;   // tuning knob
-        int P = a.N <= 128 ? 2 : (a.N <= 256 ? 4 : 8);
+        // (re-measured once the generic fallback had left the kernels: the longest per-lane arrays that are
+        // instantiated win -- N = 160: 2 lanes 75 % against 67 % with 4; N = 320: 4 lanes 73 % against 63 % with 8)
+        int P = a.N <= 160 ? 2 : (a.N <= 320 ? 4 : 8);
         if (force_p) P = force_p;
         int rc = APGPU_ERR_UNSUPPORTED;
         if (P == 2) rc = stack_dispatch_meanclip_coop_p2(frames, a, st, done_pix);
@@ -234,7 +236,7 @@ extern "C" const char* apgpu_stack_kernel_name(int N, int method, double k_lo, d
     if (N > 100 && meanclip_eligible(N, method, k_lo, k_hi, maxiters, cen, dev, flags) &&
         !(flags & (APGPU_STACK_DIRECT_LOADS | APGPU_STACK_USE_TMA | APGPU_STACK_USE_CPASYNC | APGPU_STACK_PREFER_SHARED |
                    APGPU_STACK_PREFER_REGISTERS))) {
-        if (N <= 512) snprintf(g_kname, sizeof(g_kname), "meanclip_coop<%d>", N <= 128 ? 2 : (N <= 256 ? 4 : 8));
+        if (N <= 512) snprintf(g_kname, sizeof(g_kname), "meanclip_coop<%d>", N <= 160 ? 2 : (N <= 320 ? 4 : 8));
         else snprintf(g_kname, sizeof(g_kname), "meanclip_split<8>");
         return g_kname;
     }

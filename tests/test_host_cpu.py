@@ -41,7 +41,9 @@ def test_kernel_selection_is_host_logic():
     assert kernels.stack_kernel_name(100).startswith("sorted_medmad1<100>")
     assert kernels.stack_kernel_name(100, "average", 3, 3, 5, "mean", "std") == "meanclip<100>"
     assert kernels.stack_kernel_name(100, "average", 3, 3, 5, "mean", "std", prefer="shared") == "meanclip_smem"
-    assert kernels.stack_kernel_name(300, "average", 3, 3, 5, "mean", "std") == "meanclip_coop<8>"
+    assert kernels.stack_kernel_name(300, "average", 3, 3, 5, "mean", "std") == "meanclip_coop<4>"
+    assert kernels.stack_kernel_name(400, "average", 3, 3, 5, "mean", "std") == "meanclip_coop<8>"
+    assert kernels.stack_kernel_name(150, "average", 3, 3, 5, "mean", "std") == "meanclip_coop<2>"
     assert kernels.stack_kernel_name(300, "average", 3, 3, 5, "mean", "std", prefer="shared") == "meanclip_smem"
     assert kernels.stack_kernel_name(200, "average", 3, 3, 5, "mean", "std") == "meanclip_coop<4>"
     assert kernels.stack_kernel_name(1000, "average", 3, 3, 5, "mean", "std") == "meanclip_split<8>"
