@@ -20,7 +20,7 @@
 //                       float64 by the scan launch below, so rejection maps are identical.  Fed by a warp-granular
 //                       tensor-map TMA pipeline when the frames are equally spaced
 //                       (stack_meanclip.cuh), else by direct loads / cp.async.
-//   meanclip_coop<NBL,P> the same algorithm for 100 < N <= 512: P lanes share a pixel, P warps
+//   meanclip_coop<NBL,P> the same algorithm for 128 < N <= 512: P lanes share a pixel, P warps
 //                       share a 128B-swizzled TMA tile (stack_meanclip_coop.cuh);
 //                       meanclip_split (cp.async, 512 < N <= 1024), meanclip_smem (pointer tables).
 //   sorted<NB,MODE>     register-resident Batcher merge-exchange network (N <= 200) with
@@ -46,6 +46,10 @@ enum Family { FAM_GENERIC = 0, FAM_MEANCLIP = 1, FAM_SORT_MED = 2, FAM_SORT_MEDM
               FAM_SORT_MEDUNC = 5 };
 
 constexpr int MEANCLIP_SMEM_MAX_N = 4 * ((SMEM_MAX_BYTES / (TPB * 16)) & ~1);   // 452
+// the lane-cooperative kernels take over above this frame count (re-measured after the generic fallback had left the
+// kernels: the single-thread meanclip<128> runs N = 104 / 128 at 73 % / 79 % of the roofline, 2 lanes per pixel at
+// 64 % / 72 %; from N = 144 on the cooperative kernels lead by 1-5 %)
+constexpr int MEANCLIP_COOP_MIN_N = 128;
 constexpr int MEANCLIP_REG_DEFAULT_MAX_N = 200;  // measured: the register kernel wins wherever it exists (bench.py variants)
 
 // (NLO, NB] buckets.  meanclip goes to 200 frames in registers; sorted to 128.
@@ -233,7 +237,7 @@ extern "C" const char* apgpu_stack_kernel_name(int N, int method, double k_lo, d
     Family f = choose_family(N, method, k_lo, k_hi, maxiters, cen, dev, want_uncert != 0, flags, &b);
     // long kappa-sigma stacks: the name of the default path on equally spaced frames (other layouts fall back
     // to the pointer-table kernels named below -- apgpu_stack_last_staging() tells which one ran)
-    if (N > 100 && meanclip_eligible(N, method, k_lo, k_hi, maxiters, cen, dev, flags) &&
+    if (N > MEANCLIP_COOP_MIN_N && meanclip_eligible(N, method, k_lo, k_hi, maxiters, cen, dev, flags) &&
         !(flags & (APGPU_STACK_DIRECT_LOADS | APGPU_STACK_USE_TMA | APGPU_STACK_USE_CPASYNC | APGPU_STACK_PREFER_SHARED |
                    APGPU_STACK_PREFER_REGISTERS))) {
         if (N <= 512) snprintf(g_kname, sizeof(g_kname), "meanclip_coop<%d>", N <= 160 ? 2 : (N <= 320 ? 4 : 8));
@@ -327,7 +331,7 @@ int stack_reduce_fast(const T* const* frames, int N, double k_lo, double k_hi, i
     // whatever follows only sees the (< 32-pixel) tail  (float32 frames; uint16 frames use the register
     // kernels up to N = 200)
     if constexpr (sizeof(T) == sizeof(float)) {
-        if (N > 100 && meanclip_eligible(N, method, k_lo, k_hi, maxiters, cen, dev, flags)) {
+        if (N > MEANCLIP_COOP_MIN_N && meanclip_eligible(N, method, k_lo, k_hi, maxiters, cen, dev, flags)) {
             int64_t done = 0;
             const int rc = stack_dispatch_meanclip_split(frames, a, st, flags, &done);
             if (rc != APGPU_OK && rc != APGPU_ERR_UNSUPPORTED) return rc;

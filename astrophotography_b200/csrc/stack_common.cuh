@@ -20,7 +20,7 @@
 //                       routine, so rejection maps are identical.  Fed by a warp-granular
 //                       tensor-map TMA pipeline when the frames are equally spaced
 //                       (stack_meanclip.cuh), else by direct loads / cp.async.
-//   meanclip_coop<NBL,P> the same algorithm for 100 < N <= 512: P lanes share a pixel, P warps
+//   meanclip_coop<NBL,P> the same algorithm for 128 < N <= 512: P lanes share a pixel, P warps
 //                       share a 128B-swizzled TMA tile (stack_meanclip_coop.cuh);
 //                       meanclip_split (cp.async, 512 < N <= 1024), meanclip_smem (pointer tables).
 //   sorted<NB,MODE>     register-resident Batcher merge-exchange network (N <= 200) with

@@ -207,7 +207,7 @@ def test_meanclip_tensormap_staging(cuda, n, case):
 @pytest.mark.parametrize("n", [101, 127, 128, 129, 160, 161, 199, 200, 201, 256, 257, 320, 399, 448, 512, 513, 641, 800, 1000, 1024])
 @pytest.mark.parametrize("case", [c for c in FAST_CASES if c[-1] == "meanclip"][:2], ids=lambda c: "-".join(map(str, c)))
 def test_meanclip_lane_split_long_stacks(cuda, n, case):
-    """Long stacks on equally spaced frames: 2, 4 or 8 lanes share a pixel (lane-split tensor-map kernels)."""
+    """Long stacks on equally spaced frames: above N = 128, 2, 4 or 8 lanes share a pixel (lane-split tensor-map kernels)."""
     torch = cuda
     from astrophotography_b200 import kernels
     method, k_lo, k_hi, maxiters, cen, dev, _ = case
@@ -216,7 +216,8 @@ def test_meanclip_lane_split_long_stacks(cuda, n, case):
     for out_f64 in (False, True):
         got = _run(torch, st, method=method, k_lo=k_lo, k_hi=k_hi, maxiters=maxiters, cen=cen, dev=dev,
                    out_f64=out_f64, want_uncert=True)
-        assert kernels.stack_last_staging() == (5 if n <= 512 else 4)
+        # (N <= 128: the single-thread register kernel on warp-granular tensor-map tiles leads there)
+        assert kernels.stack_last_staging() == (3 if n <= 128 else (5 if n <= 512 else 4))
         assert np.array_equal(got["nrej"].astype(np.int64), exp["nrej"])
         assert np.array_equal(got["allmasked"], exp["allmasked"])
         _assert_close_data(got["data"].astype(np.float64), exp["data"], RTOL32 if not out_f64 else 2e-7, 12.0)
