@@ -1,3 +1,5 @@
+"""Single-thread register kernel against the lane-cooperative one for kappa-sigma stacks just above N = 100
+(dev tool; decided MEANCLIP_COOP_MIN_N in csrc/stack.cu).  Usage: python tools/time_coop_boundary.py [N ...]"""
 import sys, torch
 sys.path.insert(0, "/root/repo")
 import bench
