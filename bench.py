@@ -538,7 +538,9 @@ def run_gpu(args, shape):
             "clocks": clocks, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": recorded_traffic(kname, shape), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "kernel": kname},
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel": kname,
+                         "step": "the kernel above + stack_marked_kernel, the scan launch that finishes the pixels it "
+                                 "marked (DESIGN 3.3b): `achieved` divides by the time of both, `traffic` is the sum of both"},
             "e2e": e2e, "e2e_u16": e2e_u16, "strong": strong, "cpu_baseline": cpu, "variants": variants,
         }
         print(json.dumps(line))
