@@ -194,6 +194,65 @@ def test_sigma_clip_properties():
     assert abs(med - 100) < 2 and 3 < std < 7
 
 
+def _scalar_sigma_clip_pixel(x, k_lo, k_hi, maxiters, cen, dev):
+    """astropy.stats.sigma_clip on one pixel's N samples, written out sample by sample with plain Python floats
+    (a second, structurally different restatement: no masked arrays, no axis arithmetic)."""
+    import math
+    kept = [float(v) for v in x if math.isfinite(float(v))]           # sigma_clip masks non-finite input first
+
+    def median(v):
+        w = sorted(v)
+        m = len(w)
+        return w[m // 2] if m % 2 else (w[m // 2 - 1] + w[m // 2]) / 2.0
+
+    it = 0
+    while kept and (maxiters is None or it < maxiters):
+        it += 1
+        mean = math.fsum(kept) / len(kept)
+        c = mean if cen == "mean" else median(kept)
+        if dev == "std":
+            s = math.sqrt(math.fsum((v - mean) ** 2 for v in kept) / len(kept))
+        else:
+            med = median(kept)
+            s = 1.482602218505602 * median([abs(v - med) for v in kept])
+        lo, hi = c - k_lo * s, c + k_hi * s
+        new = [v for v in kept if not (v < lo or v > hi)]
+        changed = len(new) != len(kept)
+        kept = new
+        if not changed:
+            break
+    return kept
+
+
+@pytest.mark.parametrize("case", [(5.0, 5.0, 1, "median", "mad_std"), (3.0, 3.0, 5, "mean", "std"),
+                                  (2.0, 3.5, None, "mean", "std"), (3.0, 3.0, 3, "median", "std"),
+                                  (1.5, 4.0, 2, "mean", "mad_std")], ids=str)
+def test_vectorised_oracle_equals_a_scalar_restatement(case):
+    """The numpy oracle (masked, vectorised over the image) against the per-pixel scalar restatement above, on
+    stacks with outliers, NaN / inf samples, constant and two-valued pixels: same survivors, same mean."""
+    k_lo, k_hi, maxiters, cen, dev = case
+    rng = np.random.default_rng(17)
+    n, h, w = 23, 6, 9
+    st = rng.normal(1000.0, 12.0, size=(n, h, w)).astype(np.float32)
+    hits = rng.random((n, h, w)) < 0.03
+    st[hits] += rng.uniform(100, 30000, size=int(hits.sum())).astype(np.float32)
+    st[0, 0, 0] = np.nan
+    st[5, 0, 1] = np.inf
+    st[:, 0, 2] = np.nan
+    st[:, 0, 3] = 7.0
+    st[: n // 2, 0, 4] = 5.0
+    st[n // 2:, 0, 4] = 6.0
+    got = C.combine(st, "average", k_lo, k_hi, maxiters, cen, dev)
+    for i in range(h):
+        for j in range(w):
+            kept = _scalar_sigma_clip_pixel(st[:, i, j], k_lo, k_hi, maxiters, cen, dev)
+            assert got["nrej"][i, j] == n - len(kept), (i, j)
+            if kept:
+                assert abs(got["data"][i, j] - sum(kept) / len(kept)) <= 1e-12 * abs(got["data"][i, j]), (i, j)
+            else:
+                assert np.isnan(got["data"][i, j]) and got["allmasked"][i, j] == 1
+
+
 def test_two_operation_orders_differ_only_at_ties(golden_dir):
     """``lo = c - k*s; x < lo`` (astropy, ccdproc >= 2.4) against
     ``x - c < -k*s`` (ccdproc <= 2.3).  The committed census says how often they disagree per
